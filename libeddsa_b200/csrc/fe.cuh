@@ -1,0 +1,347 @@
+// GF(2^255-19) arithmetic for sm_100a — one field element per thread, held in registers.
+//
+// Role of the reference's lib/fld.c + lib/fld.h (32-bit path: fld.c:282-531, common code
+// fld.c:540-709), re-designed for the B200 integer pipes:
+//   * 10 UNSIGNED limbs, alternating 26/25 bits (radix 2^25.5), value = sum v[i] * 2^ceil(25.5 i).
+//   * every limb product is one 32x32->64 IMAD.WIDE.U32; the x19 wrap-around and the x2 of
+//     odd*odd pairs are folded into 32-bit pre-multiplied operands, so a multiplication is exactly
+//     100 wide products (55 for a squaring) and the accumulators never leave registers.
+//   * additions / subtractions are lazy (no carry); subtraction adds a multiple of p limb-wise so
+//     limbs stay non-negative (the reference uses signed limbs instead; only canonical bytes have
+//     to agree, SURVEY.md §7 hard part 1).
+//
+// Limb bounds ("tight" = output of fe_mul/fe_sq/fe_carry):
+//   even limbs <= 2^26 + 2^13, odd limbs <= 2^25 + 2^17.
+// fe_mul(a, b):  a even <= 2^28.3, odd <= 2^27.3 ; b even <= 2^27.7, odd <= 2^26.7 (b gets the x19).
+// fe_sq(a):      a even <= 2^27.7, odd <= 2^26.7.
+// These are checked by tests/test_fe_host.py (interval test through the host build of this header).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define EDG_HD __host__ __device__ __forceinline__
+#define EDG_D __device__ __forceinline__
+#else
+#define EDG_HD static inline
+#define EDG_D static inline
+#endif
+
+namespace edg {
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct fe { u32 v[10]; };
+
+#define EDG_M26 0x3ffffffu
+#define EDG_M25 0x1ffffffu
+
+EDG_HD u64 mulw(u32 a, u32 b) { return (u64)a * (u64)b; }
+
+EDG_HD void fe_set_u32(fe &r, u32 x) {
+    r.v[0] = x;
+#pragma unroll
+    for (int i = 1; i < 10; i++) r.v[i] = 0;
+}
+
+EDG_HD void fe_copy(fe &r, const fe &a) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = a.v[i];
+}
+
+// r = a + b (lazy)                                   [reference: fld_add, fld.h:94]
+EDG_HD void fe_add(fe &r, const fe &a, const fe &b) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] + b.v[i];
+}
+
+// limbs of 2p: every limb of b that is <= these can be subtracted without going negative.
+#define EDG_2P0 0x7ffffdau   /* 2*(2^26-19) */
+#define EDG_2PE 0x7fffffeu   /* 2*(2^26-1)  */
+#define EDG_2PO 0x3fffffeu   /* 2*(2^25-1)  */
+
+// r = a - b + 2p (lazy); requires b even <= 2^27-38, b odd <= 2^26-2   [reference: fld_sub, fld.h:102]
+EDG_HD void fe_sub(fe &r, const fe &a, const fe &b) {
+    r.v[0] = a.v[0] + EDG_2P0 - b.v[0];
+#pragma unroll
+    for (int i = 1; i < 10; i++) r.v[i] = a.v[i] + ((i & 1) ? EDG_2PO : EDG_2PE) - b.v[i];
+}
+
+// r = a - b + 4p (lazy); requires b even <= 2^28-76, b odd <= 2^27-4
+EDG_HD void fe_sub4(fe &r, const fe &a, const fe &b) {
+    r.v[0] = a.v[0] + 2u * EDG_2P0 - b.v[0];
+#pragma unroll
+    for (int i = 1; i < 10; i++) r.v[i] = a.v[i] + 2u * ((i & 1) ? EDG_2PO : EDG_2PE) - b.v[i];
+}
+
+// r = 2p - a (lazy negate); requires a tight            [reference: fld_neg, fld.h:138]
+EDG_HD void fe_neg(fe &r, const fe &a) {
+    r.v[0] = EDG_2P0 - a.v[0];
+#pragma unroll
+    for (int i = 1; i < 10; i++) r.v[i] = ((i & 1) ? EDG_2PO : EDG_2PE) - a.v[i];
+}
+
+// r = 2a (lazy)                                        [reference: fld_scale2, fld.h:126]
+EDG_HD void fe_dbl(fe &r, const fe &a) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] << 1;
+}
+
+// Carry a 10-column 64-bit accumulator set down to tight limbs.  Two interleaved chains
+// (0->1->..->5 and 5->6->..->9->0->1) so that consecutive steps are independent.
+// Role of the CARRY macro, fld.c:318-330.
+EDG_HD void fe_carry64(fe &r, u64 h[10]) {
+    u64 c0, c5;
+    c0 = h[0] >> 26; h[1] += c0; h[0] &= EDG_M26;
+    c5 = h[5] >> 25; h[6] += c5; h[5] &= EDG_M25;
+    c0 = h[1] >> 25; h[2] += c0; h[1] &= EDG_M25;
+    c5 = h[6] >> 26; h[7] += c5; h[6] &= EDG_M26;
+    c0 = h[2] >> 26; h[3] += c0; h[2] &= EDG_M26;
+    c5 = h[7] >> 25; h[8] += c5; h[7] &= EDG_M25;
+    c0 = h[3] >> 25; h[4] += c0; h[3] &= EDG_M25;
+    c5 = h[8] >> 26; h[9] += c5; h[8] &= EDG_M26;
+    c0 = h[4] >> 26; h[5] += c0; h[4] &= EDG_M26;
+    c5 = h[9] >> 25; h[0] += c5 * 19u; h[9] &= EDG_M25;
+    c0 = h[5] >> 25; h[6] += c0; h[5] &= EDG_M25;
+    c5 = h[0] >> 26; h[1] += c5; h[0] &= EDG_M26;
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = (u32)h[i];
+}
+
+// Cheap 32-bit carry pass for lazily added values (limbs < 2^32): result tight.
+EDG_HD void fe_carry(fe &r, const fe &a) {
+    u32 t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = a.v[i];
+    u32 c;
+    c = t[9] >> 25; t[9] &= EDG_M25; t[0] += 19u * c;      // c < 2^7
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        if (i & 1) { c = t[i] >> 25; t[i] &= EDG_M25; }
+        else       { c = t[i] >> 26; t[i] &= EDG_M26; }
+        t[i + 1] += c;
+    }
+    // t[9] < 2^25 + 2^7 ; leave (well inside tight bound)
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = t[i];
+}
+
+// r = a * b mod p, tight output.  100 IMAD.WIDE.U32.            [reference: fld_mul, fld.c:448]
+EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+    u32 b19[10], a2[10];
+#pragma unroll
+    for (int j = 1; j < 10; j++) b19[j] = 19u * b.v[j];
+#pragma unroll
+    for (int i = 1; i < 10; i += 2) a2[i] = a.v[i] << 1;
+    u64 h[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        u64 s = 0;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+            const int j = (k - i + 10) % 10;
+            const bool wrap = i > k;
+            const bool both_odd = (i & 1) && (j & 1);
+            const u32 x = both_odd ? a2[i] : a.v[i];
+            const u32 y = wrap ? b19[j] : b.v[j];
+            s += mulw(x, y);
+        }
+        h[k] = s;
+    }
+    fe_carry64(r, h);
+}
+
+// r = a^2 mod p, tight output.  55 IMAD.WIDE.U32.                [reference: fld_sq, fld.c:503]
+EDG_HD void fe_sq(fe &r, const fe &a) {
+    // d[i] = 2 a_i ; w[j] = 19 a_j (j even) or 38 a_j (j odd) for the wrapped half
+    u32 d[10], w[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) d[i] = a.v[i] << 1;
+#pragma unroll
+    for (int j = 5; j < 10; j++) w[j] = ((j & 1) ? 38u : 19u) * a.v[j];
+    u64 h[10];
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        u64 s = 0;
+#pragma unroll
+        for (int i = 0; i < 10; i++) {
+#pragma unroll
+            for (int j = i; j < 10; j++) {
+                if ((i + j) % 10 != k) continue;
+                const bool wrap = (i + j) >= 10;
+                const bool both_odd = (i & 1) && (j & 1);
+                // coefficient of a_i a_j: (i<j ? 2 : 1) * (both_odd ? 2 : 1) * (wrap ? 19 : 1)
+                u32 x, y;
+                if (!wrap) {
+                    if (i == j) { x = both_odd ? d[i] : a.v[i]; y = a.v[j]; }
+                    else        { x = d[i]; y = both_odd ? d[j] : a.v[j]; }
+                } else {
+                    // wrap implies j >= 5; w[j] already carries 19 (j even) or 38 (j odd)
+                    const int twos = (i < j ? 1 : 0) + (both_odd ? 1 : 0) - ((j & 1) ? 1 : 0);  // 0 or 1
+                    x = twos ? d[i] : a.v[i];
+                    y = w[j];
+                }
+                s += mulw(x, y);
+            }
+        }
+        h[k] = s;
+    }
+    fe_carry64(r, h);
+}
+
+// r = a * 121665 mod p (tight a), tight output.         [reference: fld_scale, fld.c:430; only s=121665 is used, x25519.c:77]
+EDG_HD void fe_mul121665(fe &r, const fe &a) {
+    u64 h[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) h[i] = mulw(a.v[i], 121665u);
+    fe_carry64(r, h);
+}
+
+// n successive squarings
+EDG_HD void fe_sqn(fe &r, const fe &a, int n) {
+    fe_sq(r, a);
+    for (int i = 1; i < n; i++) fe_sq(r, r);
+}
+
+// Unique representative in [0, p), limbs exactly 26/25 bits.          [reference: fld_reduce, fld.c:342]
+EDG_HD void fe_canon(fe &r, const fe &a) {
+    u32 t[10];
+#pragma unroll
+    for (int i = 0; i < 10; i++) t[i] = a.v[i];
+    u32 c;
+    // two plain carry rounds bring the value into [0, 2^255 + small)
+#pragma unroll
+    for (int round = 0; round < 2; round++) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            if (i & 1) { c = t[i] >> 25; t[i] &= EDG_M25; }
+            else       { c = t[i] >> 26; t[i] &= EDG_M26; }
+            t[i + 1] += c;
+        }
+        c = t[9] >> 25; t[9] &= EDG_M25; t[0] += 19u * c;
+    }
+    // now value < 2^255 + 19*2^7 and all limbs but t[0] are in range; t[0] < 2^26 + 19*2^7.
+    // q = 1 iff value >= p  <=>  value + 19 >= 2^255 : propagate the carry of (value + 19).
+    c = (t[0] + 19u) >> 26;
+#pragma unroll
+    for (int i = 1; i < 10; i++) c = (t[i] + c) >> ((i & 1) ? 25 : 26);
+    // c is 0 or 1 (or 2 only if value >= 2^256-ish, impossible here)
+    t[0] += 19u * c;
+#pragma unroll
+    for (int i = 0; i < 9; i++) {
+        u32 cc;
+        if (i & 1) { cc = t[i] >> 25; t[i] &= EDG_M25; }
+        else       { cc = t[i] >> 26; t[i] &= EDG_M26; }
+        t[i + 1] += cc;
+    }
+    t[9] &= EDG_M25;   // drops the 2^255 that "value - p = value + 19 - 2^255" subtracts
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = t[i];
+}
+
+// 32 little-endian bytes (as 8 LE words) -> fe.  ALL 256 bits are taken; bit 255 folds in as +19
+// (SURVEY Q6).                                                        [reference: fld_import, fld.c:383]
+EDG_HD void fe_from_words(fe &r, const u32 w[8]) {
+    // limb i starts at bit offset o_i = ceil(25.5 i): 0,26,51,77,102,128,153,179,204,230
+    r.v[0] = w[0] & EDG_M26;
+    r.v[1] = ((w[0] >> 26) | (w[1] << 6)) & EDG_M25;
+    r.v[2] = ((w[1] >> 19) | (w[2] << 13)) & EDG_M26;
+    r.v[3] = ((w[2] >> 13) | (w[3] << 19)) & EDG_M25;
+    r.v[4] = (w[3] >> 6) & EDG_M26;
+    r.v[5] = w[4] & EDG_M25;
+    r.v[6] = ((w[4] >> 25) | (w[5] << 7)) & EDG_M26;
+    r.v[7] = ((w[5] >> 19) | (w[6] << 13)) & EDG_M25;
+    r.v[8] = ((w[6] >> 12) | (w[7] << 20)) & EDG_M26;
+    r.v[9] = (w[7] >> 6) & EDG_M25;
+    r.v[0] += 19u * (w[7] >> 31);
+}
+
+// fe -> canonical 32 bytes (8 LE words).                              [reference: fld_export, fld.c:406]
+EDG_HD void fe_to_words(u32 w[8], const fe &a) {
+    fe t;
+    fe_canon(t, a);
+    w[0] = t.v[0] | (t.v[1] << 26);
+    w[1] = (t.v[1] >> 6) | (t.v[2] << 19);
+    w[2] = (t.v[2] >> 13) | (t.v[3] << 13);
+    w[3] = (t.v[3] >> 19) | (t.v[4] << 6);
+    w[4] = t.v[5] | (t.v[6] << 25);
+    w[5] = (t.v[6] >> 7) | (t.v[7] << 19);
+    w[6] = (t.v[7] >> 13) | (t.v[8] << 12);
+    w[7] = (t.v[8] >> 20) | (t.v[9] << 6);
+}
+
+// 1 if a == 0 mod p else 0; branch-free.                              [reference: fld_eq, fld.c:547]
+EDG_HD u32 fe_is_zero(const fe &a) {
+    fe t;
+    fe_canon(t, a);
+    u32 x = 0;
+#pragma unroll
+    for (int i = 0; i < 10; i++) x |= t.v[i];
+    return (u32)(((u64)x - 1) >> 63);
+}
+
+// a, b tight -> 1 if equal mod p
+EDG_HD u32 fe_eq(const fe &a, const fe &b) {
+    fe t;
+    fe_sub(t, a, b);
+    return fe_is_zero(t);
+}
+
+// r = mask ? b : a  (mask all-ones or zero), branch-free   [reference: memselect, ed.c:80]
+EDG_HD void fe_select(fe &r, const fe &a, const fe &b, u32 mask) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] ^ ((a.v[i] ^ b.v[i]) & mask);
+}
+
+// conditional swap under mask (all-ones or zero), branch-free   [reference: ctmemswap, x25519.c:36]
+EDG_HD void fe_cswap(fe &a, fe &b, u32 mask) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+        u32 d = (a.v[i] ^ b.v[i]) & mask;
+        a.v[i] ^= d;
+        b.v[i] ^= d;
+    }
+}
+
+// z^(2^250 - 1) and z^11 — the shared prefix of both exponentiations.
+EDG_HD void fe_pow_2_250_m1(fe &r, fe &z11, const fe &z) {
+    fe z2, z9, t0, t1, t2;
+    fe_sq(z2, z);                 // 2
+    fe_sqn(t0, z2, 2);            // 8
+    fe_mul(z9, t0, z);            // 9
+    fe_mul(z11, z9, z2);          // 11
+    fe_sq(t0, z11);               // 22
+    fe_mul(t0, t0, z9);           // 2^5 - 1
+    fe_sqn(t1, t0, 5);
+    fe_mul(t0, t1, t0);           // 2^10 - 1
+    fe_sqn(t1, t0, 10);
+    fe_mul(t1, t1, t0);           // 2^20 - 1
+    fe_sqn(t2, t1, 20);
+    fe_mul(t1, t2, t1);           // 2^40 - 1
+    fe_sqn(t1, t1, 10);
+    fe_mul(t0, t1, t0);           // 2^50 - 1
+    fe_sqn(t1, t0, 50);
+    fe_mul(t1, t1, t0);           // 2^100 - 1
+    fe_sqn(t2, t1, 100);
+    fe_mul(t1, t2, t1);           // 2^200 - 1
+    fe_sqn(t1, t1, 50);
+    fe_mul(r, t1, t0);            // 2^250 - 1
+}
+
+// r = z^(p-2) = z^-1 (0 -> 0).  254 S + 11 M.                      [reference: fld_inv, fld.c:579]
+EDG_HD void fe_inv(fe &r, const fe &z) {
+    fe t, z11;
+    fe_pow_2_250_m1(t, z11, z);
+    fe_sqn(t, t, 5);              // 2^255 - 32
+    fe_mul(r, t, z11);            // 2^255 - 21
+}
+
+// r = z^((p-5)/8) = z^(2^252 - 3).  251 S + 11 M (z11 unused).    [reference: fld_pow2523, fld.c:658]
+EDG_HD void fe_pow2523(fe &r, const fe &z) {
+    fe t, z11;
+    fe_pow_2_250_m1(t, z11, z);
+    fe_sqn(t, t, 2);              // 2^252 - 4
+    fe_mul(r, t, z);              // 2^252 - 3
+}
+
+}  // namespace edg
