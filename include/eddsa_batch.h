@@ -1,0 +1,84 @@
+/*
+ * eddsa_batch.h — batch C-ABI of the B200-native Ed25519 / X25519 engine.
+ *
+ * N independent operations per call; item i of every array belongs to operation i and produces
+ * exactly what the single-operation function of eddsa.h produces for the same inputs (bit-exact
+ * with phlay/libeddsa v0.8, including its non-RFC behaviours).  This is the interface an FFI
+ * (cgo / JNI / ctypes ...) binds; see INTEGRATION.md.
+ *
+ * Layouts (all dense, caller-owned):
+ *   sec, pub, scalar, point, out : n x 32 bytes          sig : n x 64 bytes        ok : n bytes (0 / 1)
+ *   messages: one byte blob `msgs`; operation i signs / verifies
+ *       msgs[off[i] .. off[i+1])          if off != NULL  (n + 1 offsets, non-decreasing), else
+ *       msgs[i*fixed_len .. (i+1)*fixed_len)
+ *
+ * Host-buffer functions (…_batch): shard the batch by contiguous index ranges over the visible
+ * B200s (one host thread + streams per device, no inter-device communication), stream chunks
+ * through pinned staging buffers so copies overlap the kernels, and return when all outputs are in
+ * the caller's memory.  Caller buffers that are already page-locked are copied from directly.
+ *
+ * Device-buffer functions (…_batch_dev): all pointers are device pointers on the CURRENT CUDA device,
+ * 16-byte aligned; the work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and the
+ * call returns without synchronising.
+ *
+ * Return value: 0 on success, otherwise a nonzero error code (a cudaError_t value, or
+ * EDDSA_B200_EINVAL); on error the outputs are unspecified.  eddsa_b200_last_error() describes it.
+ * All functions may be called concurrently from several host threads.
+ */
+#ifndef EDDSA_BATCH_H
+#define EDDSA_BATCH_H
+
+#include "eddsa.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDDSA_B200_EINVAL (-1)
+
+/* ---- host buffers -------------------------------------------------------------------------- */
+/* batch of ed25519_genpub (reference eddsa.h:44, ed25519-sha512.c:73) */
+EDDSA_DECL int ed25519_genpub_batch(size_t n, uint8_t *pub, const uint8_t *sec);
+/* batch of ed25519_sign (reference eddsa.h:47, ed25519-sha512.c:129) */
+EDDSA_DECL int ed25519_sign_batch(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub,
+                                  const uint8_t *msgs, const size_t *off, size_t fixed_len);
+/* batch of ed25519_verify (reference eddsa.h:52, ed25519-sha512.c:148) */
+EDDSA_DECL int ed25519_verify_batch(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub,
+                                    const uint8_t *msgs, const size_t *off, size_t fixed_len);
+/* batch of x25519 (reference eddsa.h:67, x25519.c:215) */
+EDDSA_DECL int x25519_batch(size_t n, uint8_t *out, const uint8_t *scalar, const uint8_t *point);
+/* batch of x25519_base (reference eddsa.h:64, x25519.c:203) */
+EDDSA_DECL int x25519_base_batch(size_t n, uint8_t *out, const uint8_t *scalar);
+/* batches of the key conversions (reference eddsa.h:77,80) */
+EDDSA_DECL int pk_ed25519_to_x25519_batch(size_t n, uint8_t *out, const uint8_t *in);
+EDDSA_DECL int sk_ed25519_to_x25519_batch(size_t n, uint8_t *out, const uint8_t *in);
+
+/* ---- device buffers (current device, asynchronous on `stream`) ------------------------------- */
+EDDSA_DECL int ed25519_genpub_batch_dev(size_t n, uint8_t *pub, const uint8_t *sec, void *stream);
+EDDSA_DECL int ed25519_sign_batch_dev(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub,
+                                      const uint8_t *msgs, const uint64_t *off, size_t fixed_len, void *stream);
+EDDSA_DECL int ed25519_verify_batch_dev(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub,
+                                        const uint8_t *msgs, const uint64_t *off, size_t fixed_len, void *stream);
+EDDSA_DECL int x25519_batch_dev(size_t n, uint8_t *out, const uint8_t *scalar, const uint8_t *point, void *stream);
+EDDSA_DECL int x25519_base_batch_dev(size_t n, uint8_t *out, const uint8_t *scalar, void *stream);
+EDDSA_DECL int pk_ed25519_to_x25519_batch_dev(size_t n, uint8_t *out, const uint8_t *in, void *stream);
+EDDSA_DECL int sk_ed25519_to_x25519_batch_dev(size_t n, uint8_t *out, const uint8_t *in, void *stream);
+
+/* ---- engine control -------------------------------------------------------------------------- */
+/* Explicit initialisation (optional; every entry point initialises lazily).  Uses the devices named
+ * by the environment variable EDDSA_B200_DEVICES ("0,1,2" or a count "4"; default: all visible). */
+EDDSA_DECL int eddsa_b200_init(void);
+EDDSA_DECL void eddsa_b200_shutdown(void);
+/* number of devices the host-buffer API shards over */
+EDDSA_DECL int eddsa_b200_device_count(void);
+/* restrict the host-buffer API to the first `count` of the configured devices (0 = all) */
+EDDSA_DECL int eddsa_b200_set_device_count(int count);
+/* kernels launched by this library so far in this process (all devices) */
+EDDSA_DECL unsigned long long eddsa_b200_launch_count(void);
+/* human-readable description of the last error seen by the calling thread ("" if none) */
+EDDSA_DECL const char *eddsa_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

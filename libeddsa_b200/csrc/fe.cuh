@@ -20,10 +20,10 @@
 
 #if defined(__CUDACC__)
 #define EDG_HD __host__ __device__ __forceinline__
-#define EDG_D __device__ __forceinline__
+#define EDG_NOINLINE static __host__ __device__ __noinline__
 #else
 #define EDG_HD static inline
-#define EDG_D static inline
+#define EDG_NOINLINE static
 #endif
 
 namespace edg {
@@ -200,6 +200,7 @@ EDG_HD void fe_mul121665(fe &r, const fe &a) {
 // n successive squarings
 EDG_HD void fe_sqn(fe &r, const fe &a, int n) {
     fe_sq(r, a);
+#pragma unroll 1
     for (int i = 1; i < n; i++) fe_sq(r, r);
 }
 
@@ -303,45 +304,42 @@ EDG_HD void fe_cswap(fe &a, fe &b, u32 mask) {
     }
 }
 
-// z^(2^250 - 1) and z^11 — the shared prefix of both exponentiations.
-EDG_HD void fe_pow_2_250_m1(fe &r, fe &z11, const fe &z) {
-    fe z2, z9, t0, t1, t2;
-    fe_sq(z2, z);                 // 2
-    fe_sqn(t0, z2, 2);            // 8
-    fe_mul(z9, t0, z);            // 9
-    fe_mul(z11, z9, z2);          // 11
-    fe_sq(t0, z11);               // 22
-    fe_mul(t0, t0, z9);           // 2^5 - 1
-    fe_sqn(t1, t0, 5);
-    fe_mul(t0, t1, t0);           // 2^10 - 1
-    fe_sqn(t1, t0, 10);
-    fe_mul(t1, t1, t0);           // 2^20 - 1
-    fe_sqn(t2, t1, 20);
-    fe_mul(t1, t2, t1);           // 2^40 - 1
-    fe_sqn(t1, t1, 10);
-    fe_mul(t0, t1, t0);           // 2^50 - 1
-    fe_sqn(t1, t0, 50);
-    fe_mul(t1, t1, t0);           // 2^100 - 1
-    fe_sqn(t2, t1, 100);
-    fe_mul(t1, t2, t1);           // 2^200 - 1
-    fe_sqn(t1, t1, 50);
-    fe_mul(r, t1, t0);            // 2^250 - 1
+// Fixed exponentiations z^(p-2) (which = 1: inverse, 0 -> 0) and z^((p-5)/8) (which = 0), as ONE
+// compact, table-driven routine so that a kernel carries a single copy of the chain instead of ~20
+// inlined multiplies (instruction-cache footprint; the chain is 254 S + 11 M / 251 S + 11 M exactly as
+// in the reference).  Program step: acc = acc^(2^n) * S[m] (m = 4: no multiply), then S[st] = acc
+// (st = 4: no store).  Control flow depends only on these public constants.
+//                                                           [reference: fld_inv fld.c:579-645, fld_pow2523 fld.c:658-709]
+EDG_NOINLINE void fe_pow_chain(fe *out, const fe *zin, int which) {
+    //                                z2  z9  z11 x5  x10 x20 x40 x50 x100 x200 x250 final
+    const unsigned char prog_n[12] = {1,  2,  0,  1,  5,  10, 20, 10, 50,  100, 50,  0};
+    const unsigned char prog_m[12] = {4,  0,  1,  2,  2,  2,  3,  2,  2,   3,   2,   0};
+    const unsigned char prog_s[12] = {1,  2,  1,  2,  2,  3,  4,  2,  3,   4,   4,   4};
+    fe s0, s1, s2, s3, acc;
+    fe_copy(s0, *zin);
+    fe_copy(acc, *zin);
+    fe_copy(s1, *zin); fe_copy(s2, *zin); fe_copy(s3, *zin);
+#pragma unroll 1
+    for (int step = 0; step < 12; step++) {
+        int n = prog_n[step], m = prog_m[step];
+        const int st = prog_s[step];
+        if (step == 11) { n = which ? 5 : 2; m = which ? 1 : 0; }   // * z11 (inverse) or * z (pow2523)
+#pragma unroll 1
+        for (int i = 0; i < n; i++) fe_sq(acc, acc);
+        if (m != 4) {
+            fe t;
+            if (m == 0) fe_copy(t, s0); else if (m == 1) fe_copy(t, s1); else if (m == 2) fe_copy(t, s2); else fe_copy(t, s3);
+            fe_mul(acc, acc, t);
+        }
+        if (st == 1) fe_copy(s1, acc); else if (st == 2) fe_copy(s2, acc); else if (st == 3) fe_copy(s3, acc);
+    }
+    fe_copy(*out, acc);
 }
 
 // r = z^(p-2) = z^-1 (0 -> 0).  254 S + 11 M.                      [reference: fld_inv, fld.c:579]
-EDG_HD void fe_inv(fe &r, const fe &z) {
-    fe t, z11;
-    fe_pow_2_250_m1(t, z11, z);
-    fe_sqn(t, t, 5);              // 2^255 - 32
-    fe_mul(r, t, z11);            // 2^255 - 21
-}
+EDG_HD void fe_inv(fe &r, const fe &z) { fe_pow_chain(&r, &z, 1); }
 
-// r = z^((p-5)/8) = z^(2^252 - 3).  251 S + 11 M (z11 unused).    [reference: fld_pow2523, fld.c:658]
-EDG_HD void fe_pow2523(fe &r, const fe &z) {
-    fe t, z11;
-    fe_pow_2_250_m1(t, z11, z);
-    fe_sqn(t, t, 2);              // 2^252 - 4
-    fe_mul(r, t, z);              // 2^252 - 3
-}
+// r = z^((p-5)/8) = z^(2^252 - 3).  251 S + 11 M.                  [reference: fld_pow2523, fld.c:658]
+EDG_HD void fe_pow2523(fe &r, const fe &z) { fe_pow_chain(&r, &z, 0); }
 
 }  // namespace edg

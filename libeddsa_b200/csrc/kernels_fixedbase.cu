@@ -1,0 +1,100 @@
+// Fixed-base kernels (sm_100a): ed25519_genpub, ed25519_sign, x25519_base and sk_ed25519_to_x25519.
+// One operation per thread; the 61 440-byte signed radix-16 comb table of B is staged once per
+// persistent block in shared memory and scanned with masks (constant time: no branch or address
+// depends on a secret).  Replaces ed25519-sha512.c:53-137, 243-256 and x25519.c:158-208.
+#define EDG_TABLE_QUAL __device__ const
+#define EDG_WANT_BASE_COMB
+#include "kernel_common.cuh"
+using namespace edg;
+#include "base_table.inc"
+
+namespace {
+
+constexpr int kCombBytes = EDG_BASE_COMB_WORDS * 4;      // 61 440
+
+__global__ void __launch_bounds__(kThreads) k_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar) {
+    extern __shared__ __align__(16) u32 s_comb[];
+    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 s[8], o[8];
+        load8(s, scalar, i);
+        x25519_base_op(o, s, s_comb);
+        store8(out, i, o);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_genpub(size_t n, uint8_t *pub, const uint8_t *sec) {
+    extern __shared__ __align__(16) u32 s_comb[];
+    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 o[8];
+        ed25519_genpub_op(o, sec + 32 * i, s_comb);
+        store8(pub, i, o);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
+                                                   const unsigned long long *off, unsigned long long fixed_len) {
+    extern __shared__ __align__(16) u32 s_comb[];
+    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 p[8], o[16];
+        const uint8_t *m; u64 len;
+        msg_of(m, len, msgs, off, fixed_len, i);
+        load8(p, pub, i);
+        ed25519_sign_op(o, sec + 32 * i, p, m, len, s_comb);
+        store8(sig, 2 * i, o);
+        store8(sig, 2 * i + 1, o + 8);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_sk_convert(size_t n, uint8_t *out, const uint8_t *in) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 o[8];
+        sk_ed25519_to_x25519_op(o, in + 32 * i);
+        store8(out, i, o);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int edg_fixedbase_init(void) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_x25519_base, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_genpub, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_sign, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    return 0;
+}
+
+int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, int sm_count, void *stream) {
+    if (n == 0) return 0;
+    int g = grid_for(k_x25519_base, n, kCombBytes, sm_count, nullptr);
+    k_x25519_base<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, out, scalar);
+    return (int)cudaGetLastError();
+}
+
+int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, int sm_count, void *stream) {
+    if (n == 0) return 0;
+    int g = grid_for(k_genpub, n, kCombBytes, sm_count, nullptr);
+    k_genpub<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, pub, sec);
+    return (int)cudaGetLastError();
+}
+
+int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
+                    const unsigned long long *off, unsigned long long fixed_len, int sm_count, void *stream) {
+    if (n == 0) return 0;
+    int g = grid_for(k_sign, n, kCombBytes, sm_count, nullptr);
+    k_sign<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
+    return (int)cudaGetLastError();
+}
+
+int edg_launch_sk_convert(size_t n, uint8_t *out, const uint8_t *in, int sm_count, void *stream) {
+    if (n == 0) return 0;
+    int g = grid_for(k_sk_convert, n, 0, sm_count, nullptr);
+    k_sk_convert<<<g, kThreads, 0, (cudaStream_t)stream>>>(n, out, in);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// One complete Ed25519 / X25519 operation per thread, written as plain inline functions so the
+// same code is (a) the body of the CUDA kernels in kernels.cu and (b) compiled for the host by the
+// unit tests (tests/host_sim) — test infrastructure only; the shipped library has no CPU path.
+//
+// Reference behaviour reproduced bit-for-bit: S is reduced mod L, never range
+// checked (Q1); verify is cofactorless and compares encodings (Q2); public keys always decode (Q3);
+// t = SHA512(R||A||M) mod L fully reduced (Q4); off-curve A -> reject (Q5 policy); X25519 uses all
+// 256 bits of u (Q6), clamps itself and runs 256 ladder steps with inv(0) = 0 (Q7); sign hashes the
+// caller's pub as given (Q8); fixed-base scalars are reduced mod L first (Q9).
+#pragma once
+#include "fe.cuh"
+#include "sc.cuh"
+#include "sha512.cuh"
+#include "ge.cuh"
+
+namespace edg {
+
+// ------------------------------------------------------------------------------------------------
+// X25519 variable base: Montgomery ladder.              [do_x25519 x25519.c:129-150, mg_scale :104-123,
+//                                                         montgomery :60-94, ctmemswap :36-49]
+// Constant time: the scalar only ever feeds swap masks.
+// ------------------------------------------------------------------------------------------------
+EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
+    u32 e[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = scalar[i];
+    e[0] &= 0xfffffff8u;                                  // x25519.c:138-140
+    e[7] &= 0x7fffffffu;
+    e[7] |= 0x40000000u;
+    fe x1, x2, z2, x3, z3;
+    fe_from_words(x1, point);                             // all 256 bits, bit 255 -> +19 (Q6)   x25519.c:142
+    fe_set_u32(x2, 1); fe_set_u32(z2, 0);                 // (1 : 0)                              x25519.c:111-112
+    fe_copy(x3, x1); fe_set_u32(z3, 1);                   // (u : 1)
+    // 256 steps, most significant bit first (bit 255 is always 0 after clamping, kept for fidelity)
+#pragma unroll 1
+    for (int pos = 255; pos >= 0; pos--) {
+        // bit `pos` = top bit of e[7]; then shift the whole scalar left by one (no indexed access)
+        const u32 mask = 0u - (e[7] >> 31);
+#pragma unroll
+        for (int i = 7; i > 0; i--) e[i] = (e[i] << 1) | (e[i - 1] >> 31);
+        e[0] <<= 1;
+        fe_cswap(x2, x3, mask);
+        fe_cswap(z2, z3, mask);
+        fe sa, da, aa, bb, ee, sb, db, t1, t2;
+        fe_add(sa, x2, z2);                               // (2)
+        fe_sub(da, x2, z2);                               // (3)
+        fe_sq(aa, sa);
+        fe_sq(bb, da);
+        fe_add(sb, x3, z3);                               // (2)
+        fe_sub(db, x3, z3);                               // (3)
+        fe_mul(x2, aa, bb);                               // x2' = AA BB
+        fe_sub(ee, aa, bb);                               // E = AA - BB   (3)
+        fe_mul121665(t1, ee);
+        fe_add(t1, t1, aa);                               // AA + 121665 E (2)
+        fe_mul(z2, ee, t1);                               // z2' = E (AA + a24 E)
+        fe_mul(t1, da, sb);                               // DA (a alpha 3, b alpha 2)
+        fe_mul(t2, db, sa);                               // CB
+        fe_add(x3, t1, t2);                               // (2)
+        fe_sq(x3, x3);                                    // x3' = (DA + CB)^2
+        fe_sub(t1, t1, t2);                               // (3)
+        fe_sq(t1, t1);
+        fe_mul(z3, t1, x1);                               // z3' = x1 (DA - CB)^2
+        fe_cswap(x2, x3, mask);
+        fe_cswap(z2, z3, mask);
+    }
+    fe_inv(z2, z2);                                       // inv(0) = 0 (Q7)                     x25519.c:147
+    fe_mul(x2, x2, z2);
+    fe_to_words(out, x2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fixed-base scalar multiplication r = x * B for SECRET x in [0, L): signed radix-16 comb, one
+// table row per digit (no doublings), constant-time masked row scan.     [ed_scale_base, ed.c:397-430]
+// comb = BASE_COMB (64 rows x 8 entries x 30 words), normally staged in shared memory.
+// ------------------------------------------------------------------------------------------------
+EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
+    u32 e[8];
+    sc_recode_radix16(e, x);
+    ge_identity(r);
+#pragma unroll 1
+    for (int j = 0; j < 64; j++) {
+        const int digit = (int)(e[0] & 15u) - 8;
+#pragma unroll
+        for (int i = 0; i < 7; i++) e[i] = (e[i] >> 4) | (e[i + 1] << 28);
+        e[7] >>= 4;
+        ge_pre t;
+        ge_pre_select_ct(t, comb + j * 240, digit);
+        ge_madd(r, r, t, true);
+    }
+}
+
+// clamp as ed25519_key_setup / do_x25519_base do                    [ed25519-sha512.c:41-46, x25519.c:170-172]
+EDG_HD void clamp_words(u32 w[8]) {
+    w[0] &= 0xfffffff8u;
+    w[7] &= 0x7fffffffu;
+    w[7] |= 0x40000000u;
+}
+
+// SHA512(sk) -> clamped scalar a reduced mod L (8 words) and prefix (4 big-endian words).
+//                                                                    [ed25519_key_setup :31-47, sc_import(a,h,32) :62,:98]
+EDG_HD void ed25519_expand_key(u32 a[8], u64 prefix[4], const uint8_t *sk) {
+    u64 st[8];
+    sha512_prefixed<0>(st, (const u64 *)0, sk, 32);
+    u32 h[16];
+    sha512_state_to_le_words(h, st);
+    clamp_words(h);
+    sc_reduce256(a, h);
+#pragma unroll
+    for (int i = 0; i < 4; i++) prefix[i] = st[4 + i];
+}
+
+// pub = encode(a * B)                                                 [genpub, ed25519-sha512.c:53-67]
+EDG_HD void ed25519_genpub_op(u32 pub[8], const uint8_t *sk, const u32 *comb) {
+    u32 a[8];
+    u64 prefix[4];
+    ed25519_expand_key(a, prefix, sk);
+    ge_p3 A;
+    ge_scalarmult_base_ct(A, a, comb);
+    ge_tobytes(pub, A);
+}
+
+// sig = (R, S)                                                        [sign, ed25519-sha512.c:84-123]
+EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], const uint8_t *msg, u64 len, const u32 *comb) {
+    u32 a[8], r[8], t[8], h[16];
+    u64 pre[8], st[8];
+    ed25519_expand_key(a, pre, sk);
+    sha512_prefixed<4>(st, pre, msg, len);                // r = H(prefix || M)        :101-105
+    sha512_state_to_le_words(h, st);
+    sc_reduce512(r, h);
+    ge_p3 R;
+    ge_scalarmult_base_ct(R, r, comb);                    // R = r B                   :108-109
+    ge_tobytes(sig, R);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {                          // t = H(R || pub || M)       :112-117, pub as given (Q8)
+        pre[k] = be64_from_le_words(sig[2 * k], sig[2 * k + 1]);
+        pre[4 + k] = be64_from_le_words(pub[2 * k], pub[2 * k + 1]);
+    }
+    sha512_prefixed<8>(st, pre, msg, len);
+    sha512_state_to_le_words(h, st);
+    sc_reduce512(t, h);
+    sc_muladd(sig + 8, t, a, r);                          // S = r + t a mod L         :120-122
+}
+
+// out = u-coordinate of (clamp(scalar) mod L) * B                     [do_x25519_base, x25519.c:158-197]
+EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
+    u32 e[8], x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) e[i] = scalar[i];
+    clamp_words(e);
+    sc_reduce256(x, e);                                   // Q9
+    ge_p3 R;
+    ge_scalarmult_base_ct(R, x, comb);
+    fe u, t;
+    fe_sub(t, R.Z, R.Y);                                  // x25519.c:190-194
+    fe_inv(t, t);
+    fe_add(u, R.Z, R.Y);
+    fe_mul(u, u, t);
+    fe_to_words(out, u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Verify.                                                              [ed25519_verify, ed25519-sha512.c:148-181]
+// C = S*B + t*(-A) by Straus with fixed signed 4-bit windows over both scalars (uniform control
+// flow across the warp; the reference's vartime JSF chain ed.c:455-507 computes the same group
+// element for every on-curve A because the addition law is complete).
+//   qtab : this thread's scratch for 0..8 times (-A) in cached form, 9 x 40 words
+//   small: BASE_SMALL (0..8 times B, affine precomputed), 9 x 30 words, in shared memory
+// ------------------------------------------------------------------------------------------------
+EDG_HD void load_words8(u32 w[8], const u32 *src) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    const uint4 a = __ldg(p), b = __ldg(p + 1);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+#else
+    for (int i = 0; i < 8; i++) w[i] = src[i];
+#endif
+}
+
+// sig / pub point at this signature's 64 / 32 bytes (16-byte aligned); they are re-read where
+// needed instead of being kept live in registers across the scalar-multiplication loop.
+EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
+    u32 et[8], es[8];
+    {
+        // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
+        u64 pre[8], st[8];
+        u32 h[16], t[8];
+        load_words8(t, sig);
+        load_words8(h, pub);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            pre[k] = be64_from_le_words(t[2 * k], t[2 * k + 1]);
+            pre[4 + k] = be64_from_le_words(h[2 * k], h[2 * k + 1]);
+        }
+        sha512_prefixed<8>(st, pre, msg, len);
+        sha512_state_to_le_words(h, st);
+        sc_reduce512(t, h);
+        sc_recode_radix16(et, t);
+        load_words8(h, sig + 8);
+        sc_reduce256(t, h);                               // no range check on S (Q1)               :163
+        sc_recode_radix16(es, t);
+    }
+
+    // table k*Q for Q = -A, k = 0..8, cached form, in this thread's scratch                       :151, :174-175
+    u32 on_curve;
+    {
+        ge_p3 Q;
+        u32 a[8];
+        load_words8(a, pub);
+        on_curve = ge_frombytes(Q, a, true);
+        ge_cached c, c1;
+        fe_set_u32(c.ypx, 1); fe_set_u32(c.ymx, 1); fe_set_u32(c.z2, 2); fe_set_u32(c.t2d, 0);
+        ge_cached_store(qtab, c);
+        ge_to_cached(c1, Q);
+        ge_cached_store(qtab + 40, c1);
+#pragma unroll 1
+        for (int k = 2; k <= 8; k++) {
+            ge_add_cached(Q, Q, c1, true);                // k*Q = (k-1)*Q + Q
+            ge_to_cached(c, Q);
+            ge_cached_store(qtab + 40 * k, c);
+        }
+    }
+
+    ge_p3 R;
+    ge_identity(R);
+#pragma unroll 1
+    for (int j = 63; j >= 0; j--) {
+        const int dt = (int)(et[7] >> 28) - 8;
+        const int ds = (int)(es[7] >> 28) - 8;
+#pragma unroll
+        for (int i = 7; i > 0; i--) { et[i] = (et[i] << 4) | (et[i - 1] >> 28); es[i] = (es[i] << 4) | (es[i - 1] >> 28); }
+        et[0] <<= 4; es[0] <<= 4;
+        if (j != 63) {
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) ge_dbl(R, R, k == 3);
+        }
+        {
+            const u32 neg = (u32)(dt >> 31);
+            const u32 absd = ((u32)dt ^ neg) - neg;
+            ge_cached c;
+            ge_cached_load(c, qtab + 40 * absd);
+            ge_cached_cneg(c, neg);
+            ge_add_cached(R, R, c, true);
+        }
+        {
+            ge_pre b;
+            ge_pre_load(b, small, ds);
+            ge_madd(R, R, b, false);
+        }
+    }
+    u32 check[8], r8[8];
+    ge_tobytes(check, R);                                 // :177
+    load_words8(r8, sig);
+    u32 diff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) diff |= check[i] ^ r8[i];    // encode(C) == R bytes (Q2)            :180
+    return (diff == 0 ? 1u : 0u) & (on_curve & 1u);       // off-curve A -> reject (Q5 policy)
+}
+
+// pk_ed25519_to_x25519: u = (1 + y) / (1 - y) of the decoded point.   [ed25519-sha512.c:187-237]
+EDG_HD void pk_ed25519_to_x25519_op(u32 out[8], const u32 in[8]) {
+    ge_p3 P;
+    ge_frombytes(P, in, false);
+    fe u, t;
+    fe_add(u, P.Z, P.Y);
+    fe_sub(t, P.Z, P.Y);
+    fe_inv(t, t);
+    fe_mul(u, u, t);
+    fe_to_words(out, u);
+}
+
+// sk_ed25519_to_x25519: clamped low half of SHA512(sk).                [ed25519-sha512.c:243-256]
+EDG_HD void sk_ed25519_to_x25519_op(u32 out[8], const uint8_t *sk) {
+    u64 st[8];
+    sha512_prefixed<0>(st, (const u64 *)0, sk, 32);
+    u32 h[16];
+    sha512_state_to_le_words(h, st);
+    clamp_words(h);
+#pragma unroll
+    for (int i = 0; i < 8; i++) out[i] = h[i];
+}
+
+}  // namespace edg

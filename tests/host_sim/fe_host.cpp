@@ -19,3 +19,22 @@ void h_fe_inv(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 40); fe_
 void h_fe_pow2523(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 40); fe_pow2523(z, x); memcpy(r, z.v, 40); }
 uint32_t h_fe_is_zero(const uint32_t *a) { fe x; memcpy(x.v, a, 40); return fe_is_zero(x); }
 }
+#include "../../libeddsa_b200/csrc/sc.cuh"
+extern "C" {
+void h_sc_reduce512(uint32_t *r, const uint32_t *x) { sc_reduce512(r, x); }
+void h_sc_reduce256(uint32_t *r, const uint32_t *x) { sc_reduce256(r, x); }
+void h_sc_muladd(uint32_t *r, const uint32_t *a, const uint32_t *b, const uint32_t *c) { sc_muladd(r, a, b, c); }
+void h_sc_recode(uint32_t *e, const uint32_t *x) { sc_recode_radix16(e, x); }
+}
+#include "../../libeddsa_b200/csrc/sha512.cuh"
+extern "C" {
+// digest = SHA512(pre (npre bytes: 0, 32 or 64) || msg)
+void h_sha512(uint8_t *out, const uint8_t *pre, int npre, const uint8_t *msg, uint64_t len) {
+    u64 st[8], pw[8];
+    for (int k = 0; k < npre / 8; k++) { u32 a, b; memcpy(&a, pre + 8 * k, 4); memcpy(&b, pre + 8 * k + 4, 4); pw[k] = be64_from_le_words(a, b); }
+    if (npre == 0) sha512_prefixed<0>(st, pw, msg, len);
+    else if (npre == 32) sha512_prefixed<4>(st, pw, msg, len);
+    else sha512_prefixed<8>(st, pw, msg, len);
+    u32 x[16]; sha512_state_to_le_words(x, st); memcpy(out, x, 64);
+}
+}

@@ -1,0 +1,27 @@
+// TEST INFRASTRUCTURE ONLY: host build of the per-thread operation bodies (ops.cuh), so the exact
+// code the CUDA kernels execute can be checked against the oracle / golden fixtures without a GPU.
+// Nothing in the product links this file.
+#include <string.h>
+#include <stdint.h>
+#define EDG_TABLE_QUAL static const
+#define EDG_WANT_BASE_COMB
+#define EDG_WANT_BASE_SMALL
+#include "../../libeddsa_b200/csrc/ops.cuh"
+#include "../../libeddsa_b200/csrc/base_table.inc"
+using namespace edg;
+extern "C" {
+void hs_x25519(uint8_t *out, const uint8_t *scalar, const uint8_t *point) {
+    u32 o[8], s[8], p[8]; memcpy(s, scalar, 32); memcpy(p, point, 32); x25519_op(o, s, p); memcpy(out, o, 32);
+}
+void hs_genpub(uint8_t *pub, const uint8_t *sk) { u32 o[8]; ed25519_genpub_op(o, sk, BASE_COMB); memcpy(pub, o, 32); }
+void hs_sign(uint8_t *sig, const uint8_t *sk, const uint8_t *pub, const uint8_t *msg, uint64_t len) {
+    u32 o[16], p[8]; memcpy(p, pub, 32); ed25519_sign_op(o, sk, p, msg, len, BASE_COMB); memcpy(sig, o, 64);
+}
+int hs_verify(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64_t len) {
+    u32 s[16], p[8], qtab[360]; memcpy(s, sig, 64); memcpy(p, pub, 32);
+    return (int)ed25519_verify_op(s, p, msg, len, qtab, BASE_SMALL);
+}
+void hs_x25519_base(uint8_t *out, const uint8_t *scalar) { u32 o[8], s[8]; memcpy(s, scalar, 32); x25519_base_op(o, s, BASE_COMB); memcpy(out, o, 32); }
+void hs_pk_conv(uint8_t *out, const uint8_t *in) { u32 o[8], p[8]; memcpy(p, in, 32); pk_ed25519_to_x25519_op(o, p); memcpy(out, o, 32); }
+void hs_sk_conv(uint8_t *out, const uint8_t *in) { u32 o[8]; sk_ed25519_to_x25519_op(o, in); memcpy(out, o, 32); }
+}
