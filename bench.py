@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200-native Ed25519 / X25519 batch engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch-log2 20]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): Ed25519 verify/s, sign/s & X25519 ops/s, batch 2^20 per GPU.
+A "step" is one pass of the hot path over one synthetic batch: 2^20 independent Ed25519
+verifications of (pubkey, 64-byte message, signature) triples — BASELINE config 1's workload —
+resident in HBM.  The same protocol is then repeated for sign, x25519, genpub and x25519_base and
+reported under "also" (each with its own integer-multiply roofline fraction).
+
+  value     device-timed (CUDA events on the launching stream) whole-job ops/s, inputs resident in HBM
+  e2e       same metric through the public host-buffer C-ABI (ed25519_verify_batch) from pinned host
+            memory: H2D of sig/pub/msg and D2H of the accept flags inside the timed region
+  roofline  compute-bound on the 32x32->64 integer multiplier (IMAD.WIDE, fmaheavy pipe); peak measured
+            on this pool's B200s (profiles/r01_pipe_microbench.md): 32 wide multiplies/clk/SM
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref, kind "reference"; oracle port otherwise) on the
+            box's host cores, one instance per core, bounded sample of the same workload
+One process per GPU; batches are sharded by rank (no collective on the data path); the timed region
+is bracketed by barrier + synchronize and the max over ranks is reported.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "Ed25519 verify/s (batch 2^20 per GPU, 64 B messages); sign/s and X25519 ops/s under 'also'"
+UNIT = "ops/s"
+
+# ---- integer-multiply roofline model -------------------------------------------------
+# measured on this pool's B200 (tools/pipe_bench.cu, profiles/r01_pipe_microbench.md):
+IMAD_WIDE_PER_CLK_PER_SM = 32.0      # IMAD.WIDE.U32 thread-instructions / clk / SM (IMAD lo: 64)
+SM_COUNT = 148
+SM_MAX_MHZ = 1965.0
+PEAK_TMULS = IMAD_WIDE_PER_CLK_PER_SM * SM_COUNT * SM_MAX_MHZ * 1e6 / 1e12   # 9.31 T wide multiplies / s
+PROD_M, PROD_S = 100, 55             # wide multiplies per field multiplication / squaring (10 x 25.5-bit limbs)
+# field operations per op: reference counts (instrumented reference) and the counts
+# this engine executes (tests/test_host_sim.py::test_field_op_counts pins them)
+REF_FM = {"verify": (2291, 1514), "sign": (506, 254), "genpub": (506, 254), "x25519_base": (505, 254), "x25519": (1292, 1278)}
+OURS_FM = {"verify": (1812, 1517), "sign": (461, 254), "genpub": (461, 254), "x25519_base": (460, 254), "x25519": (1292, 1278)}
+IO_BYTES = {"verify": 64 + 32 + 64 + 1, "sign": 32 + 32 + 64 + 64, "genpub": 64, "x25519_base": 64, "x25519": 96}
+
+
+def products(fm):
+    return fm[0] * PROD_M + fm[1] * PROD_S
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        load = [s for s, p in zip(sm, pw) if p >= 0.6 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(load), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def synth_inputs(n, seed):
+    """Synthetic random keys / messages for one rank (counter-based generator, reproducible on host and device side)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    sec = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    msgs = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+    pts = rng.integers(0, 256, (n, 32), dtype=np.uint8)      # bit 255 left random, as in the reference's KAT table
+    return sec, msgs, pts
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_rates(n_sample, seconds, threads, ops=("verify",)):
+    from cpu_ref import best_cpu_impl, OP_GENPUB, OP_SIGN, OP_VERIFY, OP_X25519, OP_X25519_BASE
+    cpu = best_cpu_impl()
+    sec, msgs, pts = synth_inputs(n_sample, 0x5EED0001)
+    pub = cpu.genpub(sec)
+    sig = cpu.sign(sec, pub, msgs, fixed_len=64)
+    out = {}
+    for op in ops:
+        if op == "verify":
+            out[op] = cpu.time_op(OP_VERIFY, seconds, threads, n_sample, sig, pub, msgs, 64)
+        elif op == "sign":
+            out[op] = cpu.time_op(OP_SIGN, seconds, threads, n_sample, sec, pub, msgs, 64)
+        elif op == "genpub":
+            out[op] = cpu.time_op(OP_GENPUB, seconds, threads, n_sample, sec)
+        elif op == "x25519":
+            out[op] = cpu.time_op(OP_X25519, seconds, threads, n_sample, sec, pts)
+        elif op == "x25519_base":
+            out[op] = cpu.time_op(OP_X25519_BASE, seconds, threads, n_sample, sec)
+    return cpu.kind, out
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    from cpu_ref import best_cpu_impl, OP_VERIFY
+    cores = os.cpu_count() or 1
+    cpu = best_cpu_impl()
+    n_sample = min(1 << args.batch_log2, 4096 * cores)
+    sec, msgs, _ = synth_inputs(n_sample, 0x5EED0001)
+    pub = cpu.genpub(sec)
+    sig = cpu.sign(sec, pub, msgs, fixed_len=64)
+    for _ in range(args.warmup):
+        cpu.verify(sig, pub, msgs, fixed_len=64)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ok = cpu.verify(sig, pub, msgs, fixed_len=64)
+    dt = time.perf_counter() - t0
+    assert ok.all()
+    value = n_sample * args.steps / dt
+    sample = f"{n_sample} of the 2^{args.batch_log2} (pubkey, 64 B msg, sig) triples per step, one reference instance per core ({cores} threads)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "config": {"workload": f"ed25519_verify, 64 B messages, CPU sample of {n_sample} ops per step", "batch_per_step": n_sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": cpu.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference for the CPU arm)")
+    os.environ["EDDSA_B200_DEVICES"] = f"{local}," if world > 1 else os.environ.get("EDDSA_B200_DEVICES", "0,")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import libeddsa_b200 as ed
+    ed.init()
+
+    n = 1 << args.batch_log2
+    K, W = args.steps, max(args.warmup, 3)
+    sec, msgs, pts = synth_inputs(n, 0x5EED0001 + rank)
+
+    def pinned(a):
+        return torch.from_numpy(a).pin_memory()
+
+    h_sec, h_msg, h_pts = pinned(sec), pinned(msgs), pinned(pts)
+    d_sec, d_msg, d_pts = h_sec.to(dev), h_msg.to(dev), h_pts.to(dev)
+    d_pub = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    d_sig = torch.empty((n, 64), dtype=torch.uint8, device=dev)
+    d_ok = torch.empty((n,), dtype=torch.uint8, device=dev)
+    d_out = torch.empty((n, 32), dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    # valid triples, produced by the (parity-tested) GPU sign path
+    ed.ed25519_genpub_batch_dev(d_pub, d_sec)
+    ed.ed25519_sign_batch_dev(d_sig, d_sec, d_pub, d_msg, fixed_len=64)
+    torch.cuda.synchronize()
+
+    passes = {
+        "verify": lambda: ed.ed25519_verify_batch_dev(d_ok, d_sig, d_pub, d_msg, fixed_len=64),
+        "sign": lambda: ed.ed25519_sign_batch_dev(d_sig, d_sec, d_pub, d_msg, fixed_len=64),
+        "x25519": lambda: ed.x25519_batch_dev(d_out, d_sec, d_pts),
+        "genpub": lambda: ed.ed25519_genpub_batch_dev(d_pub, d_sec),
+        "x25519_base": lambda: ed.x25519_base_batch_dev(d_out, d_sec),
+    }
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        """W untimed + K timed steps; every step bracketed by CUDA events on the launching stream; L2 is
+        flushed (256 MB write) between steps, outside the events.  Returns (total ms, per-launch ms list)."""
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        per = [a.elapsed_time(b) for a, b in evs]
+        return max_over_ranks(sum(per)), per
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ed.launch_count()
+    total_ms, per = timed(passes["verify"], K, W)
+    launches = ed.launch_count() - launches0 - W
+    assert bool(d_ok.all().item()), "verify rejected a valid signature"
+    value = world * n * K / (total_ms * 1e-3)
+    kernel_ms = statistics.mean(per)
+
+    also = {}
+    for name in ("sign", "x25519", "genpub", "x25519_base"):
+        ms, p = timed(passes[name], K, W)
+        rate = world * n * K / (ms * 1e-3)
+        per_gpu = rate / world
+        also[name] = {"value": rate, "unit": UNIT, "ms_per_step": ms / K,
+                      "roofline_frac_executed": per_gpu * products(OURS_FM[name]) / 1e12 / PEAK_TMULS,
+                      "roofline_frac_reference_fm": per_gpu * products(REF_FM[name]) / 1e12 / PEAK_TMULS}
+    # restore valid signatures for the e2e leg (sign overwrote d_sig with identical bytes; keep it explicit)
+    torch.cuda.synchronize()
+
+    # ---- end to end through the public host-buffer C-ABI, pinned host memory --------------------------
+    h_sig, h_pub = pinned(d_sig.cpu().numpy()), pinned(d_pub.cpu().numpy())
+    h_ok = torch.empty(n, dtype=torch.uint8).pin_memory()
+    L = ed.lib()
+    import ctypes
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        rc = L.ed25519_verify_batch(n, vp(h_ok), vp(h_sig), vp(h_pub), vp(h_msg), None, 64)
+        if rc:
+            raise RuntimeError(f"ed25519_verify_batch failed: {rc} {L.eddsa_b200_last_error()}")
+
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert bool(h_ok.all().item())
+    e2e_value = world * n * K / e2e_s
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel (k_verify) ---------------------------------------------
+        per_gpu = n / (kernel_ms * 1e-3)
+        achieved = per_gpu * products(OURS_FM["verify"]) / 1e12
+        roofline = {
+            "bound": "int32-multiply (IMAD.WIDE on the fmaheavy pipe; compute-bound, see DESIGN.md §4)",
+            "kernel": "k_verify",
+            "achieved": achieved, "peak": PEAK_TMULS, "unit": "T wide-multiplies/s (32x32->64)", "frac": achieved / PEAK_TMULS,
+            "frac_reference_fm": per_gpu * products(REF_FM["verify"]) / 1e12 / PEAK_TMULS,
+            "peak_source": "measured: tools/pipe_bench.cu on this pool's B200 = 32 IMAD.WIDE/clk/SM x 148 SM x 1965 MHz (profiles/r01_pipe_microbench.md)",
+            "wide_multiplies_per_op_executed": products(OURS_FM["verify"]),
+            "wide_multiplies_per_op_reference_fm": products(REF_FM["verify"]),
+            "kernel_ms_per_launch": kernel_ms,
+            "traffic": None,
+            "hbm": {"algorithmic_bytes_per_launch": n * IO_BYTES["verify"],
+                    "achieved_gbs": n * IO_BYTES["verify"] / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak(),
+                    "note": "HBM is not the bound: <0.1 % of measured copy bandwidth"},
+        }
+        cores = os.cpu_count() or 1
+        cpu_b = None
+        if world == 1:
+            kind, rates = cpu_rates(4096 * min(cores, 16), 2.0, cores, ops=("verify", "sign", "x25519", "genpub", "x25519_base"))
+            _, single = cpu_rates(2048, 1.5, 1, ops=("verify",))
+            cpu_b = {"value": rates["verify"], "unit": UNIT, "cores": cores, "kind": kind,
+                     "sample": f"{4096 * min(cores, 16)} of the same synthetic triples, every thread looping its slice for 2.0 s (one instance per core)",
+                     "single_thread": single["verify"], "also": {k: v for k, v in rates.items() if k != "verify"}}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (radix-2^25.5 limbs, 64-bit accumulators)",
+            "data": "synthetic",
+            "config": {"workload": "ed25519_verify of 2^%d random valid (pubkey, 64 B msg, sig) triples per GPU (BASELINE config 1)" % args.batch_log2,
+                       "batch_per_gpu": n, "global_batch": n * world, "msg_len": 64, "sharding": "by rank, no collective",
+                       "l2": "inputs 168 MB > 126 MB L2 and a 256 MB flush write between timed steps"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (64 + 32 + 64), "d2h_bytes_per_step": n,
+                    "api": "ed25519_verify_batch (host buffers, pinned)", "ms_per_step": e2e_s / K * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_b, "also": also, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def hbm_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        return 6650.0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-log2", type=int, default=20)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

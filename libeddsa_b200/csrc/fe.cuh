@@ -38,6 +38,16 @@ struct fe { u32 v[10]; };
 
 EDG_HD u64 mulw(u32 a, u32 b) { return (u64)a * (u64)b; }
 
+// host-only instrumentation used by tests/host_sim to pin the field-operation counts quoted in DESIGN.md
+#if defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
+static unsigned long edg_cnt_mul = 0, edg_cnt_sq = 0;
+#define EDG_COUNT_MUL() (++edg_cnt_mul)
+#define EDG_COUNT_SQ() (++edg_cnt_sq)
+#else
+#define EDG_COUNT_MUL() ((void)0)
+#define EDG_COUNT_SQ() ((void)0)
+#endif
+
 EDG_HD void fe_set_u32(fe &r, u32 x) {
     r.v[0] = x;
 #pragma unroll
@@ -128,6 +138,7 @@ EDG_HD void fe_carry(fe &r, const fe &a) {
 
 // r = a * b mod p, tight output.  100 IMAD.WIDE.U32.            [reference: fld_mul, fld.c:448]
 EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+    EDG_COUNT_MUL();
     u32 b19[10], a2[10];
 #pragma unroll
     for (int j = 1; j < 10; j++) b19[j] = 19u * b.v[j];
@@ -153,6 +164,7 @@ EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
 
 // r = a^2 mod p, tight output.  55 IMAD.WIDE.U32.                [reference: fld_sq, fld.c:503]
 EDG_HD void fe_sq(fe &r, const fe &a) {
+    EDG_COUNT_SQ();
     // d[i] = 2 a_i ; w[j] = 19 a_j (j even) or 38 a_j (j odd) for the wrapped half
     u32 d[10], w[10];
 #pragma unroll

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <stdint.h>
 #define EDG_TABLE_QUAL static const
+#define EDG_COUNT_OPS
 #define EDG_WANT_BASE_COMB
 #define EDG_WANT_BASE_SMALL
 #include "../../libeddsa_b200/csrc/ops.cuh"
@@ -24,4 +25,5 @@ int hs_verify(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64
 void hs_x25519_base(uint8_t *out, const uint8_t *scalar) { u32 o[8], s[8]; memcpy(s, scalar, 32); x25519_base_op(o, s, BASE_COMB); memcpy(out, o, 32); }
 void hs_pk_conv(uint8_t *out, const uint8_t *in) { u32 o[8], p[8]; memcpy(p, in, 32); pk_ed25519_to_x25519_op(o, p); memcpy(out, o, 32); }
 void hs_sk_conv(uint8_t *out, const uint8_t *in) { u32 o[8]; sk_ed25519_to_x25519_op(o, in); memcpy(out, o, 32); }
+void hs_counts(unsigned long *mul, unsigned long *sq, int reset) { *mul = edg_cnt_mul; *sq = edg_cnt_sq; if (reset) edg_cnt_mul = edg_cnt_sq = 0; }
 }

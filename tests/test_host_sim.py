@@ -1,0 +1,229 @@
+"""Unit tests of the DEVICE code's arithmetic without a GPU: the .cuh headers under
+libeddsa_b200/csrc are plain C++ inline functions, so tests/host_sim compiles them for the host
+(g++) and this file checks them against Python big integers, hashlib and the golden fixtures.
+This is test infrastructure only — the shipped library contains no host build of these functions.
+"""
+import ctypes
+import hashlib
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+from edmodel import L, P
+
+HS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_sim")
+OFF = [0, 26, 51, 77, 102, 128, 153, 179, 204, 230]
+A10 = ctypes.c_uint32 * 10
+
+
+def _build(name):
+    src, so = os.path.join(HS, name + ".cpp"), os.path.join(HS, "lib" + name + ".so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def fe():
+    return _build("fe_host")
+
+
+@pytest.fixture(scope="module")
+def ops():
+    return _build("ops_host")
+
+
+def val(limbs):
+    return sum(int(x) << o for x, o in zip(limbs, OFF))
+
+
+def rnd_limbs(rng, eb, ob):
+    return [rng.randrange(0, int(2 ** (eb if i % 2 == 0 else ob))) for i in range(10)]
+
+
+def tight(l):
+    return all(x <= (2**26 + 2**13 if i % 2 == 0 else 2**25 + 2**17) for i, x in enumerate(l))
+
+
+def call(f, *args):
+    r = A10()
+    f(r, *[A10(*a) for a in args])
+    return list(r)
+
+
+def test_fe_mul_sq_bounds_and_values(fe):
+    """Products are exact mod p and come back tight, including at the documented input bounds."""
+    rng = random.Random(1)
+    for it in range(3000):
+        if it % 3 == 0:   # operands at the maximum magnitudes the point formulas produce
+            a = [int(2 ** (28.3 if i % 2 == 0 else 27.3)) - 1 - rng.randrange(3) for i in range(10)]
+            b = [int(2 ** (27.7 if i % 2 == 0 else 26.7)) - 1 - rng.randrange(3) for i in range(10)]
+        else:
+            a, b = rnd_limbs(rng, 28.3, 27.3), rnd_limbs(rng, 27.7, 26.7)
+        r = call(fe.h_fe_mul, a, b)
+        assert val(r) % P == val(a) * val(b) % P and tight(r)
+        r = call(fe.h_fe_sq, b)
+        assert val(r) % P == val(b) ** 2 % P and tight(r)
+        t = rnd_limbs(rng, 27.6, 26.6)
+        r = call(fe.h_fe_mul121665, t)
+        assert val(r) % P == val(t) * 121665 % P and tight(r)
+        z = rnd_limbs(rng, 31, 31)
+        r = call(fe.h_fe_carry, z)
+        assert val(r) % P == val(z) % P and tight(r)
+        tt = rnd_limbs(rng, 26, 25)
+        assert val(call(fe.h_fe_sub, a, tt)) % P == (val(a) - val(tt)) % P
+        assert val(call(fe.h_fe_sub4, a, b)) % P == (val(a) - val(b)) % P
+        assert val(call(fe.h_fe_neg, tt)) % P == (-val(tt)) % P
+
+
+def test_fe_canonical_bytes(fe):
+    """fld_import semantics (all 256 bits, bit 255 -> +19) and canonical export, on edge values."""
+    rng = random.Random(2)
+    edge = [0, 1, 19, P - 1, P, P + 1, P + 18, 2**255 - 20, 2**255 - 1, 2**255, 2**255 + 18, 2**256 - 1, P + 2**200]
+    for e in edge + [rng.getrandbits(256) for _ in range(2000)]:
+        r = A10()
+        fe.h_fe_from_bytes(r, e.to_bytes(32, "little"))
+        assert val(r) % P == e % P
+        out = ctypes.create_string_buffer(32)
+        fe.h_fe_to_bytes(out, r)
+        assert int.from_bytes(out.raw, "little") == e % P
+        assert fe.h_fe_is_zero(r) == (1 if e % P == 0 else 0)
+    for _ in range(2000):   # lazy limbs up to 32 bits canonicalise correctly
+        z = rnd_limbs(rng, 32, 32)
+        r = call(fe.h_fe_canon, z)
+        assert val(r) == val(z) % P and all(x < (2**26 if i % 2 == 0 else 2**25) for i, x in enumerate(r))
+
+
+def test_fe_inverse_and_pow2523(fe):
+    rng = random.Random(3)
+    for _ in range(100):
+        t = rnd_limbs(rng, 26, 25)
+        assert val(call(fe.h_fe_inv, t)) % P == pow(val(t), P - 2, P)
+        assert val(call(fe.h_fe_pow2523, t)) % P == pow(val(t), (P - 5) // 8, P)
+    assert val(call(fe.h_fe_inv, [0] * 10)) % P == 0          # inv(0) = 0
+
+
+def test_sc_reduce_muladd_recode(fe):
+    rng = random.Random(4)
+
+    def W(x, n):
+        return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+    def V(a):
+        return sum(int(x) << (32 * i) for i, x in enumerate(a))
+
+    cases = [0, 1, L - 1, L, L + 1, 2 * L, 3 * L - 1, 2**252, 2**256 - 1, 2**512 - 1, (2**512 // L) * L, (2**512 // L) * L - 1, L * L]
+    cases += [rng.getrandbits(512) for _ in range(3000)] + [rng.getrandbits(rng.randrange(1, 512)) for _ in range(1000)]
+    for x in cases:
+        r = (ctypes.c_uint32 * 8)()
+        fe.h_sc_reduce512(r, W(x, 16))
+        assert V(r) == x % L
+    for k in range(0, 17):                                     # S + kL is reduced, never rejected (Q1)
+        x = 12345 + k * L
+        if x < 2**256:
+            r = (ctypes.c_uint32 * 8)()
+            fe.h_sc_reduce256(r, W(x, 8))
+            assert V(r) == 12345
+    for _ in range(1000):
+        a, b, c = rng.getrandbits(256), rng.getrandbits(253), rng.getrandbits(256)
+        r = (ctypes.c_uint32 * 8)()
+        fe.h_sc_muladd(r, W(a, 8), W(b, 8), W(c, 8))
+        assert V(r) == (a * b + c) % L
+    for x in [0, 1, L - 1] + [rng.randrange(L) for _ in range(500)]:
+        e = (ctypes.c_uint32 * 8)()
+        fe.h_sc_recode(e, W(x, 8))
+        ds = [((V(e) >> (4 * j)) & 15) - 8 for j in range(64)]
+        assert all(-8 <= d <= 7 for d in ds) and sum(d * 16**j for j, d in enumerate(ds)) == x
+
+
+def test_sha512_prefixed_streams(fe):
+    """The register-prefix + global-message formulation equals SHA-512 of the concatenation for every
+    length around the block boundaries and for unaligned message pointers."""
+    rng = random.Random(5)
+
+    def H(pre, msg, off):
+        buf = ctypes.create_string_buffer(len(msg) + off + 32)
+        base = ctypes.addressof(buf)
+        pad = (-base) % 16 + off
+        ctypes.memmove(base + pad, msg, len(msg))
+        out = ctypes.create_string_buffer(64)
+        fe.h_sha512(out, pre, len(pre), ctypes.c_void_p(base + pad), ctypes.c_uint64(len(msg)))
+        return out.raw
+
+    for npre in (0, 32, 64):
+        for n in list(range(0, 270)) + [1023, 1024, 1025, 4096]:
+            off = rng.choice((0, 0, 1, 4, 8))
+            pre, msg = rng.randbytes(npre), rng.randbytes(n)
+            assert H(pre, msg, off) == hashlib.sha512(pre + msg).digest(), (npre, n, off)
+
+
+def test_ops_against_golden(ops):
+    """The per-thread operation bodies (ops.cuh) reproduce the reference on the fixtures."""
+    out = ctypes.create_string_buffer(32)
+    sig = ctypes.create_string_buffer(64)
+    point, scalar, result = gu.x25519_kat()
+    for i in list(range(0, 1024, 16)):
+        ops.hs_x25519(out, scalar[i].tobytes(), point[i].tobytes())
+        assert out.raw == result[i].tobytes()
+    point, scalar, result = gu.x25519_edge()
+    for i in range(len(point)):
+        ops.hs_x25519(out, scalar[i].tobytes(), point[i].tobytes())
+        assert out.raw == result[i].tobytes()
+    sec, pub, sg, msgs = gu.ed25519_kat()
+    for i in list(range(0, 1024, 37)) + [111, 112, 127, 128, 239, 240, 1023]:
+        ops.hs_genpub(out, sec[i].tobytes())
+        assert out.raw == pub[i].tobytes()
+        ops.hs_sign(sig, sec[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
+        assert sig.raw == sg[i].tobytes()
+        assert ops.hs_verify(sg[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i]))) == 1
+    bs, bo = gu.x25519_base_kat()
+    for i in range(0, len(bs), 8):
+        ops.hs_x25519_base(out, bs[i].tobytes())
+        assert out.raw == bo[i].tobytes()
+    edsk, edpk, xsk, xpk = gu.convert_kat()
+    for i in range(0, len(edsk), 4):
+        ops.hs_sk_conv(out, edsk[i].tobytes())
+        assert out.raw == xsk[i].tobytes()
+        ops.hs_pk_conv(out, edpk[i].tobytes())
+        assert out.raw == xpk[i].tobytes()
+
+
+def test_ops_adversarial_verify(ops):
+    sig, pub, msgs, cls, expect = gu.verify_adv()
+    bad = []
+    for i in range(0, len(sig), 3):
+        got = ops.hs_verify(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
+        if got != expect[i]:
+            bad.append((i, int(cls[i])))
+    assert not bad, bad[:10]
+
+
+def test_field_op_counts(ops):
+    """Field multiplications / squarings executed per operation — the figures the integer-multiply
+    roofline in bench.py and DESIGN.md §4 is computed from (reference counts: SURVEY.md §8d)."""
+    import bench
+
+    def counts():
+        m, s = ctypes.c_ulong(), ctypes.c_ulong()
+        ops.hs_counts(ctypes.byref(m), ctypes.byref(s), 1)
+        return m.value, s.value
+
+    sec, pub, sig, msgs = gu.ed25519_kat()
+    out = ctypes.create_string_buffer(64)
+    i = 100
+    counts()
+    ops.hs_genpub(out, sec[i].tobytes())
+    assert counts() == bench.OURS_FM["genpub"]
+    ops.hs_sign(out, sec[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
+    assert counts() == bench.OURS_FM["sign"]
+    assert ops.hs_verify(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i]))) == 1
+    assert counts() == bench.OURS_FM["verify"]
+    ops.hs_x25519_base(out, sec[i].tobytes())
+    assert counts() == bench.OURS_FM["x25519_base"]
+    ops.hs_x25519(out, sec[i].tobytes(), pub[i].tobytes())
+    assert counts() == bench.OURS_FM["x25519"]
+    for op, (m, s) in bench.OURS_FM.items():           # never more field work than the reference spends
+        assert m * 100 + s * 55 <= bench.REF_FM[op][0] * 100 + bench.REF_FM[op][1] * 55
