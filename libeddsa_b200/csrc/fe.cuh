@@ -20,7 +20,7 @@
 
 #if defined(__CUDACC__)
 #define EDG_HD __host__ __device__ __forceinline__
-#define EDG_NOINLINE static __host__ __device__ __noinline__
+#define EDG_NOINLINE __host__ __device__ __forceinline__   /* compact loop bodies: cheap to inline, keeps secrets off the stack */
 #else
 #define EDG_HD static inline
 #define EDG_NOINLINE static
@@ -37,6 +37,16 @@ struct fe { u32 v[10]; };
 #define EDG_M25 0x1ffffffu
 
 EDG_HD u64 mulw(u32 a, u32 b) { return (u64)a * (u64)b; }
+
+// Optimisation barrier for constant-time masks: hides from the compiler that m is 0 / ~0, so mask
+// arithmetic (x ^ ((x ^ y) & m)) can never be turned into a select, a branch or a load predicated on
+// a secret (nvcc does exactly that to naive mask idioms — see tests/ct_negative/leaky.cu).
+EDG_HD u32 ct_mask(u32 m) {
+#if defined(__CUDA_ARCH__)
+    asm volatile("" : "+r"(m));
+#endif
+    return m;
+}
 
 // host-only instrumentation used by tests/host_sim to pin the field-operation counts quoted in DESIGN.md
 #if defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
@@ -323,18 +333,22 @@ EDG_HD void fe_cswap(fe &a, fe &b, u32 mask) {
 // (st = 4: no store).  Control flow depends only on these public constants.
 //                                                           [reference: fld_inv fld.c:579-645, fld_pow2523 fld.c:658-709]
 EDG_NOINLINE void fe_pow_chain(fe *out, const fe *zin, int which) {
-    //                                z2  z9  z11 x5  x10 x20 x40 x50 x100 x200 x250 final
-    const unsigned char prog_n[12] = {1,  2,  0,  1,  5,  10, 20, 10, 50,  100, 50,  0};
-    const unsigned char prog_m[12] = {4,  0,  1,  2,  2,  2,  3,  2,  2,   3,   2,   0};
-    const unsigned char prog_s[12] = {1,  2,  1,  2,  2,  3,  4,  2,  3,   4,   4,   4};
+    // program packed into immediates (no table in local memory):     step: 0   1   2    3   4    5    6    7    8     9    10   11
+    //   squarings n                                                         1   2   0    1   5   10   20   10   50   100   50   (5|2)
+    //   multiplier slot m (4 = none)                                         4   0   1    2   2    2    3    2    2     3    2   (1|0)
+    //   store slot st (4 = none)                                             1   2   1    2   2    3    4    2    3     4    4    4
+    const u64 PROG_N_LO = 0x0a140a0501000201ULL, PROG_N_HI = 0x00326432ULL;
+    const u64 PROG_M = 0x023223222104ULL;          // 4 bits per step, step 0 in the low nibble
+    const u64 PROG_S = 0x444324322121ULL;
     fe s0, s1, s2, s3, acc;
     fe_copy(s0, *zin);
     fe_copy(acc, *zin);
     fe_copy(s1, *zin); fe_copy(s2, *zin); fe_copy(s3, *zin);
 #pragma unroll 1
     for (int step = 0; step < 12; step++) {
-        int n = prog_n[step], m = prog_m[step];
-        const int st = prog_s[step];
+        int n = (int)(((step < 8 ? PROG_N_LO >> (8 * step) : PROG_N_HI >> (8 * (step - 8)))) & 0xff);
+        int m = (int)((PROG_M >> (4 * step)) & 0xf);
+        const int st = (int)((PROG_S >> (4 * step)) & 0xf);
         if (step == 11) { n = which ? 5 : 2; m = which ? 1 : 0; }   // * z11 (inverse) or * z (pow2523)
 #pragma unroll 1
         for (int i = 0; i < n; i++) fe_sq(acc, acc);

@@ -140,14 +140,14 @@ EDG_HD void ge_pre_cneg(ge_pre &q, u32 neg) {
 // 1P..8P.  Every entry is read and folded in with a mask; no branch or address depends on digit.
 //                                                                                 [scale16, ed.c:346-391]
 EDG_HD void ge_pre_select_ct(ge_pre &t, const u32 *row, int digit) {
-    const u32 neg = (u32)(digit >> 31);                  // all-ones if digit < 0
+    const u32 neg = ct_mask((u32)(digit >> 31));         // all-ones if digit < 0
     const u32 absd = ((u32)digit ^ neg) - neg;           // 0..8
     u32 w[30];
 #pragma unroll
     for (int i = 0; i < 30; i++) w[i] = (i == 0 || i == 10) ? 1u : 0u;    // neutral element (1, 1, 0)
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const u32 m = 0u - ((((absd ^ (u32)(k + 1)) - 1u) >> 31));         // all-ones iff absd == k+1
+        const u32 m = ct_mask(0u - ((((absd ^ (u32)(k + 1)) - 1u) >> 31)));   // all-ones iff absd == k+1
 #if defined(__CUDA_ARCH__)
         // entry k starts at word 30k: 8-byte aligned -> 15 x 64-bit broadcast loads (same address in every lane)
         const uint2 *e2 = reinterpret_cast<const uint2 *>(row + 30 * k);

@@ -35,7 +35,7 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
 #pragma unroll 1
     for (int pos = 255; pos >= 0; pos--) {
         // bit `pos` = top bit of e[7]; then shift the whole scalar left by one (no indexed access)
-        const u32 mask = 0u - (e[7] >> 31);
+        const u32 mask = ct_mask(0u - (e[7] >> 31));
 #pragma unroll
         for (int i = 7; i > 0; i--) e[i] = (e[i] << 1) | (e[i - 1] >> 31);
         e[0] <<= 1;

@@ -77,7 +77,7 @@ EDG_HD void sc_reduce512(u32 r[8], const u32 x[16]) {
             t[i] = (u32)d;
             borrow = (u32)(d >> 63);
         }
-        const u32 keep = 0u - borrow;   // all-ones if v < L (keep v)
+        const u32 keep = ct_mask(0u - borrow);   // all-ones if v < L (keep v)
 #pragma unroll
         for (int i = 0; i < 9; i++) v[i] = t[i] ^ ((t[i] ^ v[i]) & keep);
     }
