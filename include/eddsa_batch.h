@@ -75,6 +75,10 @@ EDDSA_DECL int eddsa_b200_device_count(void);
 EDDSA_DECL int eddsa_b200_set_device_count(int count);
 /* kernels launched by this library so far in this process (all devices) */
 EDDSA_DECL unsigned long long eddsa_b200_launch_count(void);
+/* diagnostic: one GF(2^255-19) operation per item, executed by the device field library (op: 0 mul,
+ * 1 square, 2 add, 3 sub, 4 times 121665, 5 canonical form, 6 inverse, 7 power (p-5)/8, 8 negate);
+ * a, b, out are n x 32 little-endian bytes, any 256-bit values.  Used by the GPU unit tests. */
+EDDSA_DECL int eddsa_b200_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op);
 /* human-readable description of the last error seen by the calling thread ("" if none) */
 EDDSA_DECL const char *eddsa_b200_last_error(void);
 

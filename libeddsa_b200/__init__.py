@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libeddsa_b200.so")
+LIB_PATH = os.environ.get("LIBEDDSA_B200_SO") or os.path.join(_HERE, "libeddsa_b200.so")   # override: tuning variants only
 _lib = None
 
 ED25519_KEY_LEN = 32
@@ -64,6 +64,7 @@ def lib():
             "x25519_base_batch_dev": [sz, vp, vp, vp],
             "pk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
             "sk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
+            "eddsa_b200_fe_selftest": [sz, vp, vp, vp, ip],
             "eddsa_b200_init": [],
             "eddsa_b200_device_count": [],
             "eddsa_b200_set_device_count": [ip],
@@ -190,6 +191,14 @@ def sk_ed25519_to_x25519_batch(sk):
     sk = _arr(sk, 32, "sk")
     out = np.empty_like(sk)
     _check(lib().sk_ed25519_to_x25519_batch(len(sk), _p(out), _p(sk)), "sk_ed25519_to_x25519_batch")
+    return out
+
+
+def fe_selftest(a, b, op):
+    """Diagnostic: field operation `op` on n x 32-byte operands, executed by the device field library."""
+    a, b = _arr(a, 32, "a"), _arr(b, 32, "b")
+    out = np.empty_like(a)
+    _check(lib().eddsa_b200_fe_selftest(len(a), _p(out), _p(a), _p(b), op), "eddsa_b200_fe_selftest")
     return out
 
 

@@ -4,7 +4,7 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define EDG_QTAB_WORDS 360 /* verify: 9 cached points x 40 words of per-thread scratch */
+#define EDG_QTAB_WORDS 288 /* verify: 9 cached points x 32 words of per-thread scratch */
 
 #ifdef __cplusplus
 extern "C" {
@@ -22,6 +22,7 @@ int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *p
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
                       const unsigned long long *off, unsigned long long fixed_len, void *scratch, int sm_count, void *stream);
 int edg_launch_pk_convert(size_t n, uint8_t *out, const uint8_t *in, int sm_count, void *stream);
+int edg_launch_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op, int sm_count, void *stream);
 int edg_launch_sk_convert(size_t n, uint8_t *out, const uint8_t *in, int sm_count, void *stream);
 
 #ifdef __cplusplus

@@ -1,29 +1,43 @@
 // GF(2^255-19) arithmetic for sm_100a — one field element per thread, held in registers.
 //
-// Role of the reference's lib/fld.c + lib/fld.h (32-bit path: fld.c:282-531, common code
-// fld.c:540-709), re-designed for the B200 integer pipes:
-//   * 10 UNSIGNED limbs, alternating 26/25 bits (radix 2^25.5), value = sum v[i] * 2^ceil(25.5 i).
-//   * every limb product is one 32x32->64 IMAD.WIDE.U32; the x19 wrap-around and the x2 of
-//     odd*odd pairs are folded into 32-bit pre-multiplied operands, so a multiplication is exactly
-//     100 wide products (55 for a squaring) and the accumulators never leave registers.
-//   * additions / subtractions are lazy (no carry); subtraction adds a multiple of p limb-wise so
-//     limbs stay non-negative (the reference uses signed limbs instead; only canonical bytes have
-//     to agree, SURVEY.md §7 hard part 1).
+// Role of the reference's lib/fld.c + lib/fld.h (fld_mul fld.c:210/448, fld_sq :250/503, fld_scale
+// :184/430, fld_reduce :54/342, fld_import/export :137,163/:383,406, fld_eq :547, fld_inv :579,
+// fld_pow2523 :658, lazy add/sub/neg fld.h:94-142), re-designed for the B200 integer pipe:
 //
-// Limb bounds ("tight" = output of fe_mul/fe_sq/fe_carry):
-//   even limbs <= 2^26 + 2^13, odd limbs <= 2^25 + 2^17.
-// fe_mul(a, b):  a even <= 2^28.3, odd <= 2^27.3 ; b even <= 2^27.7, odd <= 2^26.7 (b gets the x19).
-// fe_sq(a):      a even <= 2^27.7, odd <= 2^26.7.
-// These are checked by tests/test_fe_host.py (interval test through the host build of this header).
+//   * EIGHT SATURATED 32-bit limbs (radix 2^32), value < 2^256, "weakly reduced": any representative
+//     of the residue class modulo p = 2^255-19 below 2^256 is allowed between operations; only
+//     fe_canon / fe_to_words produce the unique value in [0, p).
+//   * a multiplication is 64 IMAD.WIDE.U32 products accumulated by hardware carry chains
+//     (IMAD.WIDE.U32 Rd, Pc, a, b, Rd  /  IMAD.WIDE.U32.X ... with carry-in), organised as 16 rows of
+//     four products in an even-word and an odd-word accumulator, one 15-word merge add, and 8 more
+//     wide products that fold the high half back with 2^256 = 38 (mod p): 72 wide multiplies per
+//     multiplication, 44 per squaring (28 doubled cross products + 8 diagonal + 8 fold).
+//     Measured on B200 (tools/fe32_proto.cu, profiles/r01_pipe_microbench.md): 1.11e11 mul/s,
+//     1.54e11 sq/s per GPU = 86 % / 73 % of the IMAD.WIDE issue peak — 1.57x / 1.20x the 10 x 25.5-bit
+//     limb form this engine started with (100 / 55 wide multiplies, no carry chains).
+//   * IMAD.WIDE has half the issue rate of IMAD on this part (32 vs 64 thread-instr/clk/SM, measured),
+//     so the design minimises the NUMBER of wide multiplies; additions run on the otherwise idle
+//     ALU pipe as IADD3.X carry chains.
+//   * every carry chain is ONE asm statement so the compiler cannot schedule anything that touches the
+//     carry flag in between; the host build of this header (tests/host_sim, test infrastructure only)
+//     uses portable 64-bit arithmetic for the same functions.
+//
+// The reference uses 5x51 / 10x25.5-bit signed lazy limbs; only canonical bytes have to agree.
 #pragma once
 #include <stdint.h>
 
 #if defined(__CUDACC__)
 #define EDG_HD __host__ __device__ __forceinline__
 #define EDG_NOINLINE __host__ __device__ __forceinline__   /* compact loop bodies: cheap to inline, keeps secrets off the stack */
+#if defined(EDG_POW_NOINLINE)
+#define EDG_POW_INLINE static __host__ __device__ __noinline__
+#else
+#define EDG_POW_INLINE EDG_NOINLINE
+#endif
 #else
 #define EDG_HD static inline
 #define EDG_NOINLINE static
+#define EDG_POW_INLINE static
 #endif
 
 namespace edg {
@@ -31,10 +45,7 @@ namespace edg {
 typedef uint32_t u32;
 typedef uint64_t u64;
 
-struct fe { u32 v[10]; };
-
-#define EDG_M26 0x3ffffffu
-#define EDG_M25 0x1ffffffu
+struct fe { u32 v[8]; };
 
 EDG_HD u64 mulw(u32 a, u32 b) { return (u64)a * (u64)b; }
 
@@ -61,162 +72,250 @@ static unsigned long edg_cnt_mul = 0, edg_cnt_sq = 0;
 EDG_HD void fe_set_u32(fe &r, u32 x) {
     r.v[0] = x;
 #pragma unroll
-    for (int i = 1; i < 10; i++) r.v[i] = 0;
+    for (int i = 1; i < 8; i++) r.v[i] = 0;
 }
 
 EDG_HD void fe_copy(fe &r, const fe &a) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = a.v[i];
+    for (int i = 0; i < 8; i++) r.v[i] = a.v[i];
 }
 
-// r = a + b (lazy)                                   [reference: fld_add, fld.h:94]
-EDG_HD void fe_add(fe &r, const fe &a, const fe &b) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] + b.v[i];
-}
+// ---------------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ---------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
 
-// limbs of 2p: every limb of b that is <= these can be subtracted without going negative.
-#define EDG_2P0 0x7ffffdau   /* 2*(2^26-19) */
-#define EDG_2PE 0x7fffffeu   /* 2*(2^26-1)  */
-#define EDG_2PO 0x3fffffeu   /* 2*(2^25-1)  */
-
-// r = a - b + 2p (lazy); requires b even <= 2^27-38, b odd <= 2^26-2   [reference: fld_sub, fld.h:102]
-EDG_HD void fe_sub(fe &r, const fe &a, const fe &b) {
-    r.v[0] = a.v[0] + EDG_2P0 - b.v[0];
-#pragma unroll
-    for (int i = 1; i < 10; i++) r.v[i] = a.v[i] + ((i & 1) ? EDG_2PO : EDG_2PE) - b.v[i];
-}
-
-// r = a - b + 4p (lazy); requires b even <= 2^28-76, b odd <= 2^27-4
-EDG_HD void fe_sub4(fe &r, const fe &a, const fe &b) {
-    r.v[0] = a.v[0] + 2u * EDG_2P0 - b.v[0];
-#pragma unroll
-    for (int i = 1; i < 10; i++) r.v[i] = a.v[i] + 2u * ((i & 1) ? EDG_2PO : EDG_2PE) - b.v[i];
-}
-
-// r = 2p - a (lazy negate); requires a tight            [reference: fld_neg, fld.h:138]
-EDG_HD void fe_neg(fe &r, const fe &a) {
-    r.v[0] = EDG_2P0 - a.v[0];
-#pragma unroll
-    for (int i = 1; i < 10; i++) r.v[i] = ((i & 1) ? EDG_2PO : EDG_2PE) - a.v[i];
-}
-
-// r = 2a (lazy)                                        [reference: fld_scale2, fld.h:126]
-EDG_HD void fe_dbl(fe &r, const fe &a) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] << 1;
-}
-
-// Carry a 10-column 64-bit accumulator set down to tight limbs.  Two interleaved chains
-// (0->1->..->5 and 5->6->..->9->0->1) so that consecutive steps are independent.
-// Role of the CARRY macro, fld.c:318-330.
-EDG_HD void fe_carry64(fe &r, u64 h[10]) {
-    u64 c0, c5;
-    c0 = h[0] >> 26; h[1] += c0; h[0] &= EDG_M26;
-    c5 = h[5] >> 25; h[6] += c5; h[5] &= EDG_M25;
-    c0 = h[1] >> 25; h[2] += c0; h[1] &= EDG_M25;
-    c5 = h[6] >> 26; h[7] += c5; h[6] &= EDG_M26;
-    c0 = h[2] >> 26; h[3] += c0; h[2] &= EDG_M26;
-    c5 = h[7] >> 25; h[8] += c5; h[7] &= EDG_M25;
-    c0 = h[3] >> 25; h[4] += c0; h[3] &= EDG_M25;
-    c5 = h[8] >> 26; h[9] += c5; h[8] &= EDG_M26;
-    c0 = h[4] >> 26; h[5] += c0; h[4] &= EDG_M26;
-    c5 = h[9] >> 25; h[0] += c5 * 19u; h[9] &= EDG_M25;
-    c0 = h[5] >> 25; h[6] += c0; h[5] &= EDG_M25;
-    c5 = h[0] >> 26; h[1] += c5; h[0] &= EDG_M26;
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = (u32)h[i];
-}
-
-// Cheap 32-bit carry pass for lazily added values (limbs < 2^32): result tight.
-EDG_HD void fe_carry(fe &r, const fe &a) {
-    u32 t[10];
-#pragma unroll
-    for (int i = 0; i < 10; i++) t[i] = a.v[i];
+// r = a + b over 8 words, returns the carry out (0 / 1)
+__device__ __forceinline__ u32 add8(u32 r[8], const u32 a[8], const u32 b[8]) {
     u32 c;
-    c = t[9] >> 25; t[9] &= EDG_M25; t[0] += 19u * c;      // c < 2^7
-#pragma unroll
-    for (int i = 0; i < 9; i++) {
-        if (i & 1) { c = t[i] >> 25; t[i] &= EDG_M25; }
-        else       { c = t[i] >> 26; t[i] &= EDG_M26; }
-        t[i + 1] += c;
-    }
-    // t[9] < 2^25 + 2^7 ; leave (well inside tight bound)
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = t[i];
+    asm("add.cc.u32 %0, %9, %17; addc.cc.u32 %1, %10, %18; addc.cc.u32 %2, %11, %19; addc.cc.u32 %3, %12, %20; "
+        "addc.cc.u32 %4, %13, %21; addc.cc.u32 %5, %14, %22; addc.cc.u32 %6, %15, %23; addc.cc.u32 %7, %16, %24; addc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(c)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return c;
 }
 
-// r = a * b mod p, tight output.  100 IMAD.WIDE.U32.            [reference: fld_mul, fld.c:448]
+// r = a - b over 8 words, returns the borrow as a mask (0 / 0xffffffff)
+__device__ __forceinline__ u32 sub8(u32 r[8], const u32 a[8], const u32 b[8]) {
+    u32 bw;
+    asm("sub.cc.u32 %0, %9, %17; subc.cc.u32 %1, %10, %18; subc.cc.u32 %2, %11, %19; subc.cc.u32 %3, %12, %20; "
+        "subc.cc.u32 %4, %13, %21; subc.cc.u32 %5, %14, %22; subc.cc.u32 %6, %15, %23; subc.cc.u32 %7, %16, %24; subc.u32 %8, 0, 0;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(bw)
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]),
+          "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]), "r"(b[4]), "r"(b[5]), "r"(b[6]), "r"(b[7]));
+    return bw;
+}
+
+// r += x (one word) over 8 words, returns the carry out
+__device__ __forceinline__ u32 addw8(u32 r[8], u32 x) {
+    u32 c;
+    asm("add.cc.u32 %0, %0, %9; addc.cc.u32 %1, %1, 0; addc.cc.u32 %2, %2, 0; addc.cc.u32 %3, %3, 0; addc.cc.u32 %4, %4, 0; "
+        "addc.cc.u32 %5, %5, 0; addc.cc.u32 %6, %6, 0; addc.cc.u32 %7, %7, 0; addc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(c) : "r"(x));
+    return c;
+}
+
+// r -= x (one word) over 8 words, returns the borrow mask
+__device__ __forceinline__ u32 subw8(u32 r[8], u32 x) {
+    u32 bw;
+    asm("sub.cc.u32 %0, %0, %9; subc.cc.u32 %1, %1, 0; subc.cc.u32 %2, %2, 0; subc.cc.u32 %3, %3, 0; subc.cc.u32 %4, %4, 0; "
+        "subc.cc.u32 %5, %5, 0; subc.cc.u32 %6, %6, 0; subc.cc.u32 %7, %7, 0; subc.u32 %8, 0, 0;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "=r"(bw) : "r"(x));
+    return bw;
+}
+
+// Row of CNT products a[0], a[2], a[4], .. (stride 2) times bi, added into acc[0 .. 2 CNT) with one
+// hardware carry chain; the carry out lands in acc[2 CNT].  (IMAD.WIDE.U32 / IMAD.WIDE.U32.X in SASS.)
+template <int CNT> __device__ __forceinline__ void cmad(u32 *acc, const u32 *a, u32 bi);
+template <> __device__ __forceinline__ void cmad<0>(u32 *, const u32 *, u32) {}
+template <> __device__ __forceinline__ void cmad<1>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a[0]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmad<2>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1; madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3; addc.u32 %4, %4, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a[0]), "r"(a[2]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmad<3>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %7, %10, %0; madc.hi.cc.u32 %1, %7, %10, %1; madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3; "
+        "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5; addc.u32 %6, %6, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmad<4>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %9, %13, %0; madc.hi.cc.u32 %1, %9, %13, %1; madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3; "
+        "madc.lo.cc.u32 %4, %11, %13, %4; madc.hi.cc.u32 %5, %11, %13, %5; madc.lo.cc.u32 %6, %12, %13, %6; madc.hi.cc.u32 %7, %12, %13, %7; "
+        "addc.u32 %8, %8, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+}
+
+// w[1..15] += od[0..14]: merge of the odd-word accumulator, one carry chain
+__device__ __forceinline__ void merge_odd(u32 *w, const u32 *od) {
+    asm("add.cc.u32 %0, %0, %15; addc.cc.u32 %1, %1, %16; addc.cc.u32 %2, %2, %17; addc.cc.u32 %3, %3, %18; addc.cc.u32 %4, %4, %19; "
+        "addc.cc.u32 %5, %5, %20; addc.cc.u32 %6, %6, %21; addc.cc.u32 %7, %7, %22; addc.cc.u32 %8, %8, %23; addc.cc.u32 %9, %9, %24; "
+        "addc.cc.u32 %10, %10, %25; addc.cc.u32 %11, %11, %26; addc.cc.u32 %12, %12, %27; addc.cc.u32 %13, %13, %28; addc.u32 %14, %14, %29;"
+        : "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]),
+          "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]),
+          "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+}
+
+// w[0..15] += diag(a_i^2 at word 2i): the 8 diagonal squares of a squaring, one carry chain
+__device__ __forceinline__ void add_squares(u32 *w, const u32 *a) {
+    asm("mad.lo.cc.u32 %0, %16, %16, %0; madc.hi.cc.u32 %1, %16, %16, %1; madc.lo.cc.u32 %2, %17, %17, %2; madc.hi.cc.u32 %3, %17, %17, %3; "
+        "madc.lo.cc.u32 %4, %18, %18, %4; madc.hi.cc.u32 %5, %18, %18, %5; madc.lo.cc.u32 %6, %19, %19, %6; madc.hi.cc.u32 %7, %19, %19, %7; "
+        "madc.lo.cc.u32 %8, %20, %20, %8; madc.hi.cc.u32 %9, %20, %20, %9; madc.lo.cc.u32 %10, %21, %21, %10; madc.hi.cc.u32 %11, %21, %21, %11; "
+        "madc.lo.cc.u32 %12, %22, %22, %12; madc.hi.cc.u32 %13, %22, %22, %13; madc.lo.cc.u32 %14, %23, %23, %14; madc.hi.u32 %15, %23, %23, %15;"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]),
+          "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]));
+}
+
+#else   // ------------------------------ host build (tests only): same functions, portable arithmetic
+
+static inline u32 add8(u32 r[8], const u32 a[8], const u32 b[8]) {
+    u64 c = 0;
+    for (int i = 0; i < 8; i++) { u64 t = (u64)a[i] + b[i] + c; r[i] = (u32)t; c = t >> 32; }
+    return (u32)c;
+}
+static inline u32 sub8(u32 r[8], const u32 a[8], const u32 b[8]) {
+    u64 bw = 0;
+    for (int i = 0; i < 8; i++) { u64 t = (u64)a[i] - b[i] - bw; r[i] = (u32)t; bw = (t >> 63) & 1; }
+    return (u32)(0 - bw);
+}
+static inline u32 addw8(u32 r[8], u32 x) {
+    u64 c = x;
+    for (int i = 0; i < 8; i++) { u64 t = (u64)r[i] + c; r[i] = (u32)t; c = t >> 32; }
+    return (u32)c;
+}
+static inline u32 subw8(u32 r[8], u32 x) {
+    u64 bw = x;
+    for (int i = 0; i < 8; i++) { u64 t = (u64)r[i] - bw; r[i] = (u32)t; bw = (t >> 63) & 1; }
+    return (u32)(0 - bw);
+}
+
+#endif
+
+// w (16 words, < 2^512) -> r = lo + 38 hi, weakly reduced.  8 wide multiplies.
+EDG_HD void fe_fold512(fe &r, const u32 w[16]) {
+    u64 c = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const u64 t = mulw(w[8 + j], 38u) + w[j] + c;
+        r.v[j] = (u32)t;
+        c = t >> 32;
+    }
+    // c <= 38: fold it once more; if that wraps past 2^256 the wrapped value is tiny, so +38 cannot carry again
+    const u32 c2 = addw8(r.v, (u32)c * 38u);
+    r.v[0] += 38u & (0u - c2);
+}
+
+// r = a + b                                            [reference: fld_add, fld.h:94]
+EDG_HD void fe_add(fe &r, const fe &a, const fe &b) {
+    u32 t[8];
+    const u32 c = add8(t, a.v, b.v);
+    const u32 c2 = addw8(t, 38u & (0u - c));           // 2^256 = 38 (mod p)
+    t[0] += 38u & (0u - c2);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+
+// r = a - b                                            [reference: fld_sub, fld.h:102]
+EDG_HD void fe_sub(fe &r, const fe &a, const fe &b) {
+    u32 t[8];
+    const u32 bw = sub8(t, a.v, b.v);                   // borrow: t = a - b + 2^256, so take 38 off again
+    const u32 bw2 = subw8(t, 38u & bw);
+    t[0] -= 38u & bw2;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
+}
+
+EDG_HD void fe_sub4(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }     // (no lazy limbs any more)
+
+// r = -a                                               [reference: fld_neg, fld.h:138]
+EDG_HD void fe_neg(fe &r, const fe &a) {
+    fe z;
+    fe_set_u32(z, 0);
+    fe_sub(r, z, a);
+}
+
+// r = 2a                                               [reference: fld_scale2, fld.h:126]
+EDG_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
+
+EDG_HD void fe_carry(fe &r, const fe &a) { fe_copy(r, a); }                   // kept for the point formulas' sake: nothing to carry
+
+// r = a * b mod p.  72 IMAD.WIDE.U32.                            [reference: fld_mul, fld.c:210 / :448]
 EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
     EDG_COUNT_MUL();
-    u32 b19[10], a2[10];
+    u32 w[17];
+#if defined(__CUDA_ARCH__)
+    // product a_j b_i lives at word i + j: even words accumulate in w[i+j], odd words in od[i+j-1]
+    u32 od[17];
 #pragma unroll
-    for (int j = 1; j < 10; j++) b19[j] = 19u * b.v[j];
+    for (int i = 0; i < 17; i++) w[i] = od[i] = 0;
 #pragma unroll
-    for (int i = 1; i < 10; i += 2) a2[i] = a.v[i] << 1;
-    u64 h[10];
-#pragma unroll
-    for (int k = 0; k < 10; k++) {
-        u64 s = 0;
-#pragma unroll
-        for (int i = 0; i < 10; i++) {
-            const int j = (k - i + 10) % 10;
-            const bool wrap = i > k;
-            const bool both_odd = (i & 1) && (j & 1);
-            const u32 x = both_odd ? a2[i] : a.v[i];
-            const u32 y = wrap ? b19[j] : b.v[j];
-            s += mulw(x, y);
-        }
-        h[k] = s;
+    for (int i = 0; i < 8; i++) {
+        if ((i & 1) == 0) { cmad<4>(w + i, a.v, b.v[i]); cmad<4>(od + i, a.v + 1, b.v[i]); }
+        else              { cmad<4>(w + i + 1, a.v + 1, b.v[i]); cmad<4>(od + i - 1, a.v, b.v[i]); }
     }
-    fe_carry64(r, h);
+    merge_odd(w, od);
+#else
+    for (int i = 0; i < 17; i++) w[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 8; j++) { const u64 t = mulw(a.v[j], b.v[i]) + w[i + j] + c; w[i + j] = (u32)t; c = t >> 32; }
+        w[i + 8] = (u32)c;
+    }
+#endif
+    fe_fold512(r, w);
 }
 
-// r = a^2 mod p, tight output.  55 IMAD.WIDE.U32.                [reference: fld_sq, fld.c:503]
+// r = a^2 mod p.  44 IMAD.WIDE.U32 (28 cross products, doubled by a 1-bit shift, + 8 squares + 8 fold).
+//                                                                  [reference: fld_sq, fld.c:250 / :503]
 EDG_HD void fe_sq(fe &r, const fe &a) {
     EDG_COUNT_SQ();
-    // d[i] = 2 a_i ; w[j] = 19 a_j (j even) or 38 a_j (j odd) for the wrapped half
-    u32 d[10], w[10];
+    u32 w[17];
+#if defined(__CUDA_ARCH__)
+    u32 od[17];
 #pragma unroll
-    for (int i = 0; i < 10; i++) d[i] = a.v[i] << 1;
+    for (int i = 0; i < 17; i++) w[i] = od[i] = 0;
+    // cross products a_j a_i, j > i:  j = i+1, i+3, .. -> odd word i+j  -> od[2i + 0, 2, ..]
+    //                                 j = i+2, i+4, .. -> even word i+j -> w[2i + 2, ..]
+#define EDG_SQ_ROW(i) cmad<(8 - (i)) / 2>(od + 2 * (i), a.v + (i) + 1, a.v[i]); cmad<(7 - (i)) / 2>(w + 2 * (i) + 2, a.v + (i) + 2, a.v[i]);
+    EDG_SQ_ROW(0) EDG_SQ_ROW(1) EDG_SQ_ROW(2) EDG_SQ_ROW(3) EDG_SQ_ROW(4) EDG_SQ_ROW(5) EDG_SQ_ROW(6)
+#undef EDG_SQ_ROW
+    merge_odd(w, od);
 #pragma unroll
-    for (int j = 5; j < 10; j++) w[j] = ((j & 1) ? 38u : 19u) * a.v[j];
-    u64 h[10];
-#pragma unroll
-    for (int k = 0; k < 10; k++) {
-        u64 s = 0;
-#pragma unroll
-        for (int i = 0; i < 10; i++) {
-#pragma unroll
-            for (int j = i; j < 10; j++) {
-                if ((i + j) % 10 != k) continue;
-                const bool wrap = (i + j) >= 10;
-                const bool both_odd = (i & 1) && (j & 1);
-                // coefficient of a_i a_j: (i<j ? 2 : 1) * (both_odd ? 2 : 1) * (wrap ? 19 : 1)
-                u32 x, y;
-                if (!wrap) {
-                    if (i == j) { x = both_odd ? d[i] : a.v[i]; y = a.v[j]; }
-                    else        { x = d[i]; y = both_odd ? d[j] : a.v[j]; }
-                } else {
-                    // wrap implies j >= 5; w[j] already carries 19 (j even) or 38 (j odd)
-                    const int twos = (i < j ? 1 : 0) + (both_odd ? 1 : 0) - ((j & 1) ? 1 : 0);  // 0 or 1
-                    x = twos ? d[i] : a.v[i];
-                    y = w[j];
-                }
-                s += mulw(x, y);
-            }
-        }
-        h[k] = s;
+    for (int k = 15; k > 0; k--) w[k] = (w[k] << 1) | (w[k - 1] >> 31);        // x2 (word 0 holds no cross product)
+    w[0] = 0;
+    add_squares(w, a.v);
+#else
+    for (int i = 0; i < 17; i++) w[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        u64 c = 0;
+        for (int j = 0; j < 8; j++) { const u64 t = mulw(a.v[j], a.v[i]) + w[i + j] + c; w[i + j] = (u32)t; c = t >> 32; }
+        w[i + 8] = (u32)c;
     }
-    fe_carry64(r, h);
+#endif
+    fe_fold512(r, w);
 }
 
-// r = a * 121665 mod p (tight a), tight output.         [reference: fld_scale, fld.c:430; only s=121665 is used, x25519.c:77]
+// r = a * 121665 mod p.                     [reference: fld_scale, fld.c:184/:430; only s = 121665 is used, x25519.c:77]
 EDG_HD void fe_mul121665(fe &r, const fe &a) {
-    u64 h[10];
+    u64 c = 0;
+    u32 t[8];
 #pragma unroll
-    for (int i = 0; i < 10; i++) h[i] = mulw(a.v[i], 121665u);
-    fe_carry64(r, h);
+    for (int j = 0; j < 8; j++) {
+        const u64 p = mulw(a.v[j], 121665u) + c;
+        t[j] = (u32)p;
+        c = p >> 32;
+    }
+    const u32 c2 = addw8(t, (u32)c * 38u);             // c < 2^17
+    t[0] += 38u & (0u - c2);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = t[i];
 }
 
 // n successive squarings
@@ -226,84 +325,55 @@ EDG_HD void fe_sqn(fe &r, const fe &a, int n) {
     for (int i = 1; i < n; i++) fe_sq(r, r);
 }
 
-// Unique representative in [0, p), limbs exactly 26/25 bits.          [reference: fld_reduce, fld.c:342]
+// Unique representative in [0, p).  Branch-free.                        [reference: fld_reduce, fld.c:54 / :342]
 EDG_HD void fe_canon(fe &r, const fe &a) {
-    u32 t[10];
+    u32 t[8];
 #pragma unroll
-    for (int i = 0; i < 10; i++) t[i] = a.v[i];
-    u32 c;
-    // two plain carry rounds bring the value into [0, 2^255 + small)
+    for (int i = 0; i < 8; i++) t[i] = a.v[i];
+    // fold bit 255 twice: value < 2^256 -> < 2^255 + 19 -> < 2^255
 #pragma unroll
     for (int round = 0; round < 2; round++) {
-#pragma unroll
-        for (int i = 0; i < 9; i++) {
-            if (i & 1) { c = t[i] >> 25; t[i] &= EDG_M25; }
-            else       { c = t[i] >> 26; t[i] &= EDG_M26; }
-            t[i + 1] += c;
-        }
-        c = t[9] >> 25; t[9] &= EDG_M25; t[0] += 19u * c;
+        const u32 top = t[7] >> 31;
+        t[7] &= 0x7fffffffu;
+        addw8(t, 19u & (0u - top));
     }
-    // now value < 2^255 + 19*2^7 and all limbs but t[0] are in range; t[0] < 2^26 + 19*2^7.
-    // q = 1 iff value >= p  <=>  value + 19 >= 2^255 : propagate the carry of (value + 19).
-    c = (t[0] + 19u) >> 26;
+    // now t < 2^255: subtract p iff t >= p  <=>  t + 19 has bit 255 set
+    u32 s[8];
 #pragma unroll
-    for (int i = 1; i < 10; i++) c = (t[i] + c) >> ((i & 1) ? 25 : 26);
-    // c is 0 or 1 (or 2 only if value >= 2^256-ish, impossible here)
-    t[0] += 19u * c;
+    for (int i = 0; i < 8; i++) s[i] = t[i];
+    addw8(s, 19u);
+    const u32 ge = ct_mask(0u - (s[7] >> 31));
+    s[7] &= 0x7fffffffu;
 #pragma unroll
-    for (int i = 0; i < 9; i++) {
-        u32 cc;
-        if (i & 1) { cc = t[i] >> 25; t[i] &= EDG_M25; }
-        else       { cc = t[i] >> 26; t[i] &= EDG_M26; }
-        t[i + 1] += cc;
-    }
-    t[9] &= EDG_M25;   // drops the 2^255 that "value - p = value + 19 - 2^255" subtracts
-#pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = t[i];
+    for (int i = 0; i < 8; i++) r.v[i] = t[i] ^ ((t[i] ^ s[i]) & ge);
 }
 
-// 32 little-endian bytes (as 8 LE words) -> fe.  ALL 256 bits are taken; bit 255 folds in as +19
-// (SURVEY Q6).                                                        [reference: fld_import, fld.c:383]
+// 32 little-endian bytes (8 LE words) -> fe.  ALL 256 bits are taken, i.e. the value is the 256-bit integer
+// modulo p, exactly what the reference computes by folding bit 255 in as +19.
+//                                                                        [reference: fld_import, fld.c:137 / :383]
 EDG_HD void fe_from_words(fe &r, const u32 w[8]) {
-    // limb i starts at bit offset o_i = ceil(25.5 i): 0,26,51,77,102,128,153,179,204,230
-    r.v[0] = w[0] & EDG_M26;
-    r.v[1] = ((w[0] >> 26) | (w[1] << 6)) & EDG_M25;
-    r.v[2] = ((w[1] >> 19) | (w[2] << 13)) & EDG_M26;
-    r.v[3] = ((w[2] >> 13) | (w[3] << 19)) & EDG_M25;
-    r.v[4] = (w[3] >> 6) & EDG_M26;
-    r.v[5] = w[4] & EDG_M25;
-    r.v[6] = ((w[4] >> 25) | (w[5] << 7)) & EDG_M26;
-    r.v[7] = ((w[5] >> 19) | (w[6] << 13)) & EDG_M25;
-    r.v[8] = ((w[6] >> 12) | (w[7] << 20)) & EDG_M26;
-    r.v[9] = (w[7] >> 6) & EDG_M25;
-    r.v[0] += 19u * (w[7] >> 31);
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = w[i];
 }
 
-// fe -> canonical 32 bytes (8 LE words).                              [reference: fld_export, fld.c:406]
+// fe -> canonical 32 bytes (8 LE words).                                [reference: fld_export, fld.c:163 / :406]
 EDG_HD void fe_to_words(u32 w[8], const fe &a) {
     fe t;
     fe_canon(t, a);
-    w[0] = t.v[0] | (t.v[1] << 26);
-    w[1] = (t.v[1] >> 6) | (t.v[2] << 19);
-    w[2] = (t.v[2] >> 13) | (t.v[3] << 13);
-    w[3] = (t.v[3] >> 19) | (t.v[4] << 6);
-    w[4] = t.v[5] | (t.v[6] << 25);
-    w[5] = (t.v[6] >> 7) | (t.v[7] << 19);
-    w[6] = (t.v[7] >> 13) | (t.v[8] << 12);
-    w[7] = (t.v[8] >> 20) | (t.v[9] << 6);
+#pragma unroll
+    for (int i = 0; i < 8; i++) w[i] = t.v[i];
 }
 
-// 1 if a == 0 mod p else 0; branch-free.                              [reference: fld_eq, fld.c:547]
+// 1 if a == 0 mod p else 0; branch-free.                                [reference: fld_eq, fld.c:547]
 EDG_HD u32 fe_is_zero(const fe &a) {
     fe t;
     fe_canon(t, a);
     u32 x = 0;
 #pragma unroll
-    for (int i = 0; i < 10; i++) x |= t.v[i];
+    for (int i = 0; i < 8; i++) x |= t.v[i];
     return (u32)(((u64)x - 1) >> 63);
 }
 
-// a, b tight -> 1 if equal mod p
 EDG_HD u32 fe_eq(const fe &a, const fe &b) {
     fe t;
     fe_sub(t, a, b);
@@ -313,14 +383,14 @@ EDG_HD u32 fe_eq(const fe &a, const fe &b) {
 // r = mask ? b : a  (mask all-ones or zero), branch-free   [reference: memselect, ed.c:80]
 EDG_HD void fe_select(fe &r, const fe &a, const fe &b, u32 mask) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) r.v[i] = a.v[i] ^ ((a.v[i] ^ b.v[i]) & mask);
+    for (int i = 0; i < 8; i++) r.v[i] = a.v[i] ^ ((a.v[i] ^ b.v[i]) & mask);
 }
 
 // conditional swap under mask (all-ones or zero), branch-free   [reference: ctmemswap, x25519.c:36]
 EDG_HD void fe_cswap(fe &a, fe &b, u32 mask) {
 #pragma unroll
-    for (int i = 0; i < 10; i++) {
-        u32 d = (a.v[i] ^ b.v[i]) & mask;
+    for (int i = 0; i < 8; i++) {
+        const u32 d = (a.v[i] ^ b.v[i]) & mask;
         a.v[i] ^= d;
         b.v[i] ^= d;
     }
@@ -332,7 +402,7 @@ EDG_HD void fe_cswap(fe &a, fe &b, u32 mask) {
 // in the reference).  Program step: acc = acc^(2^n) * S[m] (m = 4: no multiply), then S[st] = acc
 // (st = 4: no store).  Control flow depends only on these public constants.
 //                                                           [reference: fld_inv fld.c:579-645, fld_pow2523 fld.c:658-709]
-EDG_NOINLINE void fe_pow_chain(fe *out, const fe *zin, int which) {
+EDG_POW_INLINE void fe_pow_chain(fe *out, const fe *zin, int which) {
     // program packed into immediates (no table in local memory):     step: 0   1   2    3   4    5    6    7    8     9    10   11
     //   squarings n                                                         1   2   0    1   5   10   20   10   50   100   50   (5|2)
     //   multiplier slot m (4 = none)                                         4   0   1    2   2    2    3    2    2     3    2   (1|0)

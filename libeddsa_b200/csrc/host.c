@@ -31,7 +31,7 @@
 #define EDG_ALIGN 256
 #define EDG_MAX_USER_STREAMS 16
 
-typedef enum { OP_GENPUB, OP_SIGN, OP_VERIFY, OP_X25519, OP_X25519_BASE, OP_PK_CONV, OP_SK_CONV } edg_op_t;
+typedef enum { OP_GENPUB, OP_SIGN, OP_VERIFY, OP_X25519, OP_X25519_BASE, OP_PK_CONV, OP_SK_CONV, OP_FE_TEST } edg_op_t;
 
 typedef struct {
     edg_op_t op;
@@ -217,6 +217,7 @@ static int launch(edg_dev_t *c, edg_op_t op, size_t n, uint8_t *d_out, uint8_t *
     case OP_X25519_BASE: rc = edg_launch_x25519_base(n, d_out, d_in[0], c->sm_count, stream); break;
     case OP_PK_CONV: rc = edg_launch_pk_convert(n, d_out, d_in[0], c->sm_count, stream); break;
     case OP_SK_CONV: rc = edg_launch_sk_convert(n, d_out, d_in[0], c->sm_count, stream); break;
+    case OP_FE_TEST: rc = edg_launch_fe_selftest(n, d_out, d_in[0], d_in[1], (int)fixed_len, c->sm_count, stream); break;
     default: return fail(EDDSA_B200_EINVAL, "unknown operation");
     }
     if (rc) return fail(rc, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
@@ -427,6 +428,14 @@ int pk_ed25519_to_x25519_batch(size_t n, uint8_t *out, const uint8_t *in)
 int sk_ed25519_to_x25519_batch(size_t n, uint8_t *out, const uint8_t *in)
 {
     edg_job_t j = {OP_SK_CONV, n, 1, {in, NULL, NULL}, {32, 0, 0}, 0, NULL, NULL, 0, out, 32};
+    return run_job(&j);
+}
+
+/* diagnostic: one GF(2^255-19) operation per item on the device (op: 0 mul, 1 sq, 2 add, 3 sub, 4 x121665,
+ * 5 canonical form, 6 inverse, 7 ^((p-5)/8), 8 negate); a, b, out: n x 32 bytes, any 256-bit values */
+int eddsa_b200_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op)
+{
+    edg_job_t j = {OP_FE_TEST, n, 2, {a, b, NULL}, {32, 32, 0}, 0, NULL, NULL, (size_t)op, out, 32};
     return run_job(&j);
 }
 

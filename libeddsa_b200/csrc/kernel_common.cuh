@@ -7,7 +7,10 @@
 
 namespace edg {
 
-constexpr int kThreads = 128;
+#ifndef EDG_THREADS
+#define EDG_THREADS 128
+#endif
+constexpr int kThreads = EDG_THREADS;
 
 __device__ __forceinline__ void load8(u32 w[8], const uint8_t *base, size_t i) {
     load_words8(w, reinterpret_cast<const u32 *>(base + 32 * i));

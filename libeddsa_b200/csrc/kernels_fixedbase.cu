@@ -1,5 +1,5 @@
 // Fixed-base kernels (sm_100a): ed25519_genpub, ed25519_sign, x25519_base and sk_ed25519_to_x25519.
-// One operation per thread; the 61 440-byte signed radix-16 comb table of B is staged once per
+// One operation per thread; the 49 152-byte signed radix-16 comb table of B is staged once per
 // persistent block in shared memory and scanned with masks (constant time: no branch or address
 // depends on a secret).  Replaces ed25519-sha512.c:53-137, 243-256 and x25519.c:158-208.
 #define EDG_TABLE_QUAL __device__ const
@@ -8,11 +8,20 @@
 using namespace edg;
 #include "base_table.inc"
 
+#ifndef EDG_LB_X25519_BASE
+#define EDG_LB_X25519_BASE 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#endif
+#ifndef EDG_LB_GENPUB
+#define EDG_LB_GENPUB 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#endif
+#ifndef EDG_LB_SIGN
+#define EDG_LB_SIGN 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#endif
 namespace {
 
-constexpr int kCombBytes = EDG_BASE_COMB_WORDS * 4;      // 61 440
+constexpr int kCombBytes = EDG_BASE_COMB_WORDS * 4;      // 49 152
 
-__global__ void __launch_bounds__(kThreads) k_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar) {
+__global__ void __launch_bounds__(kThreads, EDG_LB_X25519_BASE) k_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -23,7 +32,7 @@ __global__ void __launch_bounds__(kThreads) k_x25519_base(size_t n, uint8_t *out
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_genpub(size_t n, uint8_t *pub, const uint8_t *sec) {
+__global__ void __launch_bounds__(kThreads, EDG_LB_GENPUB) k_genpub(size_t n, uint8_t *pub, const uint8_t *sec) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -33,7 +42,7 @@ __global__ void __launch_bounds__(kThreads) k_genpub(size_t n, uint8_t *pub, con
     }
 }
 
-__global__ void __launch_bounds__(kThreads) k_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
+__global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
                                                    const unsigned long long *off, unsigned long long fixed_len) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);

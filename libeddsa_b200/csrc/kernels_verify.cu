@@ -9,9 +9,12 @@
 using namespace edg;
 #include "base_table.inc"
 
+#ifndef EDG_LB_VERIFY
+#define EDG_LB_VERIFY 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#endif
 namespace {
 
-__global__ void __launch_bounds__(kThreads) k_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
                                                      const unsigned long long *off, unsigned long long fixed_len, u32 *scratch) {
     __shared__ __align__(16) u32 s_small[EDG_BASE_SMALL_WORDS + 2];
     stage_table(s_small, BASE_SMALL, EDG_BASE_SMALL_WORDS);

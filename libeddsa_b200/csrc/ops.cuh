@@ -42,22 +42,22 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
         fe_cswap(x2, x3, mask);
         fe_cswap(z2, z3, mask);
         fe sa, da, aa, bb, ee, sb, db, t1, t2;
-        fe_add(sa, x2, z2);                               // (2)
-        fe_sub(da, x2, z2);                               // (3)
+        fe_add(sa, x2, z2);
+        fe_sub(da, x2, z2);
         fe_sq(aa, sa);
         fe_sq(bb, da);
-        fe_add(sb, x3, z3);                               // (2)
-        fe_sub(db, x3, z3);                               // (3)
+        fe_add(sb, x3, z3);
+        fe_sub(db, x3, z3);
         fe_mul(x2, aa, bb);                               // x2' = AA BB
         fe_sub(ee, aa, bb);                               // E = AA - BB   (3)
         fe_mul121665(t1, ee);
         fe_add(t1, t1, aa);                               // AA + 121665 E (2)
         fe_mul(z2, ee, t1);                               // z2' = E (AA + a24 E)
-        fe_mul(t1, da, sb);                               // DA (a alpha 3, b alpha 2)
+        fe_mul(t1, da, sb);                               // DA
         fe_mul(t2, db, sa);                               // CB
-        fe_add(x3, t1, t2);                               // (2)
+        fe_add(x3, t1, t2);
         fe_sq(x3, x3);                                    // x3' = (DA + CB)^2
-        fe_sub(t1, t1, t2);                               // (3)
+        fe_sub(t1, t1, t2);
         fe_sq(t1, t1);
         fe_mul(z3, t1, x1);                               // z3' = x1 (DA - CB)^2
         fe_cswap(x2, x3, mask);
@@ -71,7 +71,7 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
 // ------------------------------------------------------------------------------------------------
 // Fixed-base scalar multiplication r = x * B for SECRET x in [0, L): signed radix-16 comb, one
 // table row per digit (no doublings), constant-time masked row scan.     [ed_scale_base, ed.c:397-430]
-// comb = BASE_COMB (64 rows x 8 entries x 30 words), normally staged in shared memory.
+// comb = BASE_COMB (64 rows x 8 entries x 24 words = 49 152 bytes), staged in shared memory.
 // ------------------------------------------------------------------------------------------------
 EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
     u32 e[8];
@@ -84,7 +84,7 @@ EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
         for (int i = 0; i < 7; i++) e[i] = (e[i] >> 4) | (e[i + 1] << 28);
         e[7] >>= 4;
         ge_pre t;
-        ge_pre_select_ct(t, comb + j * 240, digit);
+        ge_pre_select_ct(t, comb + j * 192, digit);
         ge_madd(r, r, t, true);
     }
 }
@@ -163,8 +163,8 @@ EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
 // C = S*B + t*(-A) by Straus with fixed signed 4-bit windows over both scalars (uniform control
 // flow across the warp; the reference's vartime JSF chain ed.c:455-507 computes the same group
 // element for every on-curve A because the addition law is complete).
-//   qtab : this thread's scratch for 0..8 times (-A) in cached form, 9 x 40 words
-//   small: BASE_SMALL (0..8 times B, affine precomputed), 9 x 30 words, in shared memory
+//   qtab : this thread's scratch for 0..8 times (-A) in cached form, 9 x 32 words
+//   small: BASE_SMALL (0..8 times B, affine precomputed), 9 x EDG_SMALL_STRIDE words, in shared memory
 // ------------------------------------------------------------------------------------------------
 EDG_HD void load_words8(u32 w[8], const u32 *src) {
 #if defined(__CUDA_ARCH__)
@@ -211,12 +211,12 @@ EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg,
         fe_set_u32(c.ypx, 1); fe_set_u32(c.ymx, 1); fe_set_u32(c.z2, 2); fe_set_u32(c.t2d, 0);
         ge_cached_store(qtab, c);
         ge_to_cached(c1, Q);
-        ge_cached_store(qtab + 40, c1);
+        ge_cached_store(qtab + 32, c1);
 #pragma unroll 1
         for (int k = 2; k <= 8; k++) {
             ge_add_cached(Q, Q, c1, true);                // k*Q = (k-1)*Q + Q
             ge_to_cached(c, Q);
-            ge_cached_store(qtab + 40 * k, c);
+            ge_cached_store(qtab + 32 * k, c);
         }
     }
 
@@ -237,7 +237,7 @@ EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg,
             const u32 neg = (u32)(dt >> 31);
             const u32 absd = ((u32)dt ^ neg) - neg;
             ge_cached c;
-            ge_cached_load(c, qtab + 40 * absd);
+            ge_cached_load(c, qtab + 32 * absd);
             ge_cached_cneg(c, neg);
             ge_add_cached(R, R, c, true);
         }

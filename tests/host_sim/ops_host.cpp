@@ -19,7 +19,7 @@ void hs_sign(uint8_t *sig, const uint8_t *sk, const uint8_t *pub, const uint8_t 
     u32 o[16], p[8]; memcpy(p, pub, 32); ed25519_sign_op(o, sk, p, msg, len, BASE_COMB); memcpy(sig, o, 64);
 }
 int hs_verify(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64_t len) {
-    u32 s[16], p[8], qtab[360]; memcpy(s, sig, 64); memcpy(p, pub, 32);
+    u32 s[16], p[8], qtab[288]; memcpy(s, sig, 64); memcpy(p, pub, 32);
     return (int)ed25519_verify_op(s, p, msg, len, qtab, BASE_SMALL);
 }
 void hs_x25519_base(uint8_t *out, const uint8_t *scalar) { u32 o[8], s[8]; memcpy(s, scalar, 32); x25519_base_op(o, s, BASE_COMB); memcpy(out, o, 32); }

@@ -27,7 +27,7 @@ def test_secret_kernels_are_constant_time(libpath):
     for r in results:
         assert "error" not in r, r
         assert r["secret_loads"] > 0, f"{r['kernel']}: the audit saw no secret loads (taint source not found)"
-        assert r["instructions_on_secret_data"] > 0.5 * r["instructions"], r["kernel"]
+        assert r["instructions_on_secret_data"] > 0.3 * r["instructions"], r["kernel"]
         assert r["reached"] > 0.95 * r["instructions"], r["kernel"]
         assert not r["stack_holds_secrets"], f"{r['kernel']}: secrets spilled to local memory"
         assert r["violations"] == [], (r["kernel"], r["violations"][:5])

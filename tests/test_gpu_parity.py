@@ -19,6 +19,38 @@ def rand_bytes(rng, *shape):
     return rng.integers(0, 256, shape, dtype=np.uint8)
 
 
+# ------------------------------------------------------------------------------------------------ field arithmetic
+def test_device_field_arithmetic(ed):
+    """The PTX carry-chain field library (fe.cuh) against Python big integers, on every combination of
+    the corner values (0, p, 2p, 2^256-1, values whose fold carries twice ...) and random 256-bit inputs."""
+    from edmodel import P
+    rng = np.random.default_rng(42)
+    edge = [0, 1, 2, 19, 37, 38, 39, P - 1, P, P + 1, P + 18, 2 * P, 2 * P + 1, 2 * P + 37, 2**255 - 20, 2**255 - 1, 2**255, 2**255 + 18,
+            2**256 - 39, 2**256 - 38, 2**256 - 1, 2**256 - 2**32, 2**224, 2**32 - 1, (2**256 - 1) // 3, 2**128 - 1, 2**255 - 19 + 2**32]
+    vals_a = [x for x in edge for _ in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(20000)]
+    vals_b = [y for _ in edge for y in edge] + [int.from_bytes(rng.bytes(32), "little") for _ in range(20000)]
+    a = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vals_a), np.uint8).reshape(-1, 32)
+    b = np.frombuffer(b"".join(v.to_bytes(32, "little") for v in vals_b), np.uint8).reshape(-1, 32)
+
+    def run(op):
+        out = ed.fe_selftest(a, b, op)
+        return [int.from_bytes(out[i].tobytes(), "little") for i in range(len(out))]
+
+    for op, fn in ((0, lambda x, y: x * y), (1, lambda x, y: x * x), (2, lambda x, y: x + y), (3, lambda x, y: x - y),
+                   (4, lambda x, y: x * 121665), (8, lambda x, y: -x)):
+        got = run(op)
+        bad = [i for i in range(len(got)) if got[i] % P != fn(vals_a[i], vals_b[i]) % P]
+        assert not bad, (op, bad[:5])
+    got = run(5)
+    assert all(got[i] == vals_a[i] % P for i in range(len(got)))            # canonical form is THE value in [0, p)
+    n_small = 3000
+    a, b = a[:n_small], b[:n_small]
+    got = run(6)
+    assert all(got[i] % P == pow(vals_a[i] % P, P - 2, P) for i in range(n_small))     # inv(0) = 0 included
+    got = run(7)
+    assert all(got[i] % P == pow(vals_a[i] % P, (P - 5) // 8, P) for i in range(n_small))
+
+
 # ------------------------------------------------------------------------------------------------ fixtures
 def test_x25519_reference_kat_table(ed):
     point, scalar, result = gu.x25519_kat()

@@ -16,8 +16,7 @@ import golden_util as gu
 from edmodel import L, P
 
 HS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_sim")
-OFF = [0, 26, 51, 77, 102, 128, 153, 179, 204, 230]
-A10 = ctypes.c_uint32 * 10
+A8 = ctypes.c_uint32 * 8
 
 
 def _build(name):
@@ -36,74 +35,62 @@ def ops():
     return _build("ops_host")
 
 
-def val(limbs):
-    return sum(int(x) << o for x, o in zip(limbs, OFF))
+def val(words):
+    return sum(int(x) << (32 * i) for i, x in enumerate(words))
 
 
-def rnd_limbs(rng, eb, ob):
-    return [rng.randrange(0, int(2 ** (eb if i % 2 == 0 else ob))) for i in range(10)]
-
-
-def tight(l):
-    return all(x <= (2**26 + 2**13 if i % 2 == 0 else 2**25 + 2**17) for i, x in enumerate(l))
+def W8(x):
+    return [(x >> (32 * i)) & 0xFFFFFFFF for i in range(8)]
 
 
 def call(f, *args):
-    r = A10()
-    f(r, *[A10(*a) for a in args])
+    r = A8()
+    f(r, *[A8(*a) for a in args])
     return list(r)
 
 
-def test_fe_mul_sq_bounds_and_values(fe):
-    """Products are exact mod p and come back tight, including at the documented input bounds."""
+EDGE = [0, 1, 2, 19, 37, 38, 39, P - 1, P, P + 1, P + 18, 2 * P, 2 * P + 1, 2 * P + 37, 2**255 - 20, 2**255 - 1, 2**255, 2**255 + 18,
+        2**256 - 39, 2**256 - 38, 2**256 - 1, 2**256 - 2**32, 2**224, 2**32 - 1]
+
+
+def test_fe_arithmetic_on_all_256_bit_inputs(fe):
+    """Operands are any values < 2^256 (weakly reduced); results are exact modulo p and again < 2^256,
+    including the all-ones / near-2p / near-2^256 corner cases where the folding carries twice."""
     rng = random.Random(1)
-    for it in range(3000):
-        if it % 3 == 0:   # operands at the maximum magnitudes the point formulas produce
-            a = [int(2 ** (28.3 if i % 2 == 0 else 27.3)) - 1 - rng.randrange(3) for i in range(10)]
-            b = [int(2 ** (27.7 if i % 2 == 0 else 26.7)) - 1 - rng.randrange(3) for i in range(10)]
-        else:
-            a, b = rnd_limbs(rng, 28.3, 27.3), rnd_limbs(rng, 27.7, 26.7)
-        r = call(fe.h_fe_mul, a, b)
-        assert val(r) % P == val(a) * val(b) % P and tight(r)
-        r = call(fe.h_fe_sq, b)
-        assert val(r) % P == val(b) ** 2 % P and tight(r)
-        t = rnd_limbs(rng, 27.6, 26.6)
-        r = call(fe.h_fe_mul121665, t)
-        assert val(r) % P == val(t) * 121665 % P and tight(r)
-        z = rnd_limbs(rng, 31, 31)
-        r = call(fe.h_fe_carry, z)
-        assert val(r) % P == val(z) % P and tight(r)
-        tt = rnd_limbs(rng, 26, 25)
-        assert val(call(fe.h_fe_sub, a, tt)) % P == (val(a) - val(tt)) % P
-        assert val(call(fe.h_fe_sub4, a, b)) % P == (val(a) - val(b)) % P
-        assert val(call(fe.h_fe_neg, tt)) % P == (-val(tt)) % P
+    cases = [(a, b) for a in EDGE for b in EDGE] + [(rng.getrandbits(256), rng.getrandbits(256)) for _ in range(3000)]
+    for a, b in cases:
+        A, B = W8(a), W8(b)
+        assert val(call(fe.h_fe_mul, A, B)) % P == a * b % P
+        assert val(call(fe.h_fe_sq, A)) % P == a * a % P
+        assert val(call(fe.h_fe_mul121665, A)) % P == a * 121665 % P
+        assert val(call(fe.h_fe_sub, A, B)) % P == (a - b) % P
+        assert val(call(fe.h_fe_sub4, A, B)) % P == (a - b) % P
+        assert val(call(fe.h_fe_add, A, B)) % P == (a + b) % P
+        assert val(call(fe.h_fe_neg, A)) % P == (-a) % P
+        assert val(call(fe.h_fe_carry, A)) % P == a % P
 
 
 def test_fe_canonical_bytes(fe):
-    """fld_import semantics (all 256 bits, bit 255 -> +19) and canonical export, on edge values."""
+    """fld_import semantics (all 256 bits, bit 255 -> +19, i.e. the integer mod p) and canonical export."""
     rng = random.Random(2)
-    edge = [0, 1, 19, P - 1, P, P + 1, P + 18, 2**255 - 20, 2**255 - 1, 2**255, 2**255 + 18, 2**256 - 1, P + 2**200]
-    for e in edge + [rng.getrandbits(256) for _ in range(2000)]:
-        r = A10()
+    for e in EDGE + [rng.getrandbits(256) for _ in range(3000)]:
+        r = A8()
         fe.h_fe_from_bytes(r, e.to_bytes(32, "little"))
         assert val(r) % P == e % P
         out = ctypes.create_string_buffer(32)
         fe.h_fe_to_bytes(out, r)
         assert int.from_bytes(out.raw, "little") == e % P
         assert fe.h_fe_is_zero(r) == (1 if e % P == 0 else 0)
-    for _ in range(2000):   # lazy limbs up to 32 bits canonicalise correctly
-        z = rnd_limbs(rng, 32, 32)
-        r = call(fe.h_fe_canon, z)
-        assert val(r) == val(z) % P and all(x < (2**26 if i % 2 == 0 else 2**25) for i, x in enumerate(r))
+        assert val(call(fe.h_fe_canon, W8(e))) == e % P
 
 
 def test_fe_inverse_and_pow2523(fe):
     rng = random.Random(3)
-    for _ in range(100):
-        t = rnd_limbs(rng, 26, 25)
-        assert val(call(fe.h_fe_inv, t)) % P == pow(val(t), P - 2, P)
-        assert val(call(fe.h_fe_pow2523, t)) % P == pow(val(t), (P - 5) // 8, P)
-    assert val(call(fe.h_fe_inv, [0] * 10)) % P == 0          # inv(0) = 0 (SURVEY Q7)
+    for t in [1, 2, P - 1, P + 5, 2**256 - 1] + [rng.getrandbits(256) for _ in range(100)]:
+        assert val(call(fe.h_fe_inv, W8(t))) % P == pow(t % P, P - 2, P)
+        assert val(call(fe.h_fe_pow2523, W8(t))) % P == pow(t % P, (P - 5) // 8, P)
+    for z in (0, P, 2 * P):                                   # inv(0) = 0 for every representative of 0 (SURVEY Q7)
+        assert val(call(fe.h_fe_inv, W8(z))) % P == 0
 
 
 def test_sc_reduce_muladd_recode(fe):

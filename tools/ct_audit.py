@@ -47,7 +47,20 @@ SECRET_PARAMS = {
 PUBLIC_KERNELS = ["k_verify", "k_pk_convert"]
 
 PTR = "ptr"     # derived from a secret POINTER parameter (an address, not itself secret)
-SEC = "sec"     # secret data
+SEC = 0xFFFFFFFF  # secret data: taint is a 32-bit mask of the bits that may depend on a secret, so that
+                  # predicates ptxas packs into spare bits of a general register (@P LOP3 R, R, 0x10 ... /
+                  # LOP3 P, RZ, R, 0x2000) are tracked bit by bit instead of poisoning each other
+
+
+def is_sec(v):
+    return isinstance(v, int) and v != 0
+
+
+def tjoin(a, b):
+    """least upper bound of two taint values (None < PTR < bit masks ordered by inclusion)"""
+    if is_sec(a) or is_sec(b):
+        return (a if is_sec(a) else 0) | (b if is_sec(b) else 0)
+    return a or b
 
 BRANCH_OPS = ("BRA", "BRX", "JMP", "JMX", "CALL", "RET", "EXIT", "BREAK", "BSYNC", "WARPSYNC", "YIELD", "NANOSLEEP", "KILL", "BPT", "RTT")
 MEM_OPS = ("LDG", "STG", "LDS", "STS", "LDL", "STL", "LD", "ST", "ATOM", "ATOMS", "ATOMG", "RED", "LDSM", "LDGSTS", "LDGDEPBAR", "CCTL")
@@ -320,7 +333,7 @@ def audit(name, insns, secret_offsets, verbose=False):
             if isinstance(r, tuple):
                 continue
             if out.get(r) != v:
-                nv = SEC if SEC in (out.get(r), v) else (v or out.get(r))
+                nv = tjoin(out.get(r), v)
                 if out.get(r) != nv:
                     out[r] = nv
                     changed = True
@@ -338,7 +351,7 @@ def audit(name, insns, secret_offsets, verbose=False):
         st = dict(state[k])
         base = ins.op.split(".")[0]
         dests, srcs, addr, data = classify(ins)
-        guard_t = get(st, ins.guard) if ins.guard else None
+        guard_t = st.get(ins.guard) if ins.guard else None
 
         def rd(r):
             # value seen on THIS instruction's guard path: a half-write under the same predicate and
@@ -349,11 +362,23 @@ def audit(name, insns, secret_offsets, verbose=False):
             return st.get(r)
 
         def taint_of(names):
-            kinds = {rd(r) for r in names}
-            if SEC in kinds:
+            kinds = [rd(r) for r in names]
+            if any(is_sec(k_) for k_ in kinds):
                 return SEC
             if PTR in kinds:
                 return PTR
+            return None
+
+        def lop3_imm():
+            """(source register, immediate, lut) of `LOP3.LUT [P,] Rd, Ra, imm, RZ, lut, !PT`, else None"""
+            if not ins.op.startswith("LOP3"):
+                return None
+            ops_ = [t for t in ins.operands]
+            while ops_ and re.match(r"^U?P(\d+|T)$", ops_[0]):
+                ops_ = ops_[1:]
+            if len(ops_) >= 5 and re.match(r"^R\d+$|^RZ$", ops_[0]) and re.match(r"^R\d+(\.reuse)?$", ops_[1]) \
+                    and re.match(r"^0x[0-9a-f]+$", ops_[2]) and ops_[3] == "RZ" and re.match(r"^0x[0-9a-f]+$", ops_[4]):
+                return ops_[1].split(".")[0], int(ops_[2], 16), int(ops_[4], 16)
             return None
 
         # constant-bank reads of a secret pointer parameter
@@ -369,18 +394,18 @@ def audit(name, insns, secret_offsets, verbose=False):
 
         # ---- sinks
         if base in BRANCH_OPS or base == "BSSY":
-            bad = [r for r in ([ins.guard] if ins.guard else []) + srcs if get(st, r) == SEC]
+            bad = [r for r in ([ins.guard] if ins.guard else []) + srcs if is_sec(rd(r))]
             if bad:
                 flag(ins, "secret-dependent control flow", bad)
             if base == "BRX" or base == "JMX":
                 flag(ins, "indirect branch (not analysable)", srcs)
         if base in MEM_OPS or base in ("LDC", "ULDC", "LDCU"):
-            bad = [r for r in addr + ([ins.guard] if ins.guard else []) if get(st, r) == SEC]
+            bad = [r for r in addr + ([ins.guard] if ins.guard else []) if is_sec(rd(r))]
             if bad:
                 flag(ins, "secret-dependent memory address / predicate", bad)
-            if base in ("STS",) and taint_of(data) == SEC:
+            if base in ("STS",) and is_sec(taint_of(data)):
                 flag(ins, "secret stored to shared memory", data)
-        if base in VARLAT_OPS and taint_of(srcs) == SEC:
+        if base in VARLAT_OPS and is_sec(taint_of(srcs)):
             flag(ins, "variable-latency instruction on secret data", srcs)
 
         # ---- transfer
@@ -394,7 +419,7 @@ def audit(name, insns, secret_offsets, verbose=False):
         elif base in ("LDC", "ULDC", "LDCU"):
             new = PTR if reads_secret_param else None
         elif base in ("STL",):
-            if taint_of(data) == SEC and not stack_secret[0]:
+            if is_sec(taint_of(data)) and not stack_secret[0]:
                 stack_secret[0] = True
                 # stack became secret: re-run everything that loads from the stack
                 for j, other in enumerate(insns):
@@ -405,26 +430,46 @@ def audit(name, insns, secret_offsets, verbose=False):
             new = None
         else:
             new = taint_of(srcs)
-            if reads_secret_param and new != SEC:
+            li = lop3_imm()
+            pred_new = new
+            if li is not None:
+                ra, imm, lut = li
+                tv = rd(ra)
+                bits = tv if is_sec(tv) else 0
+                if lut == 0xC0:                      # Ra & imm
+                    bits &= imm
+                elif lut in (0xFC, 0x3C):            # Ra | imm, Ra ^ imm: the constant bits carry no secret
+                    pass
+                else:
+                    bits = SEC if bits else 0
+                new = bits if bits else (PTR if tv == PTR else None)
+                pred_new = new                        # P = (result != 0)
+            if reads_secret_param and not is_sec(new):
                 new = PTR
         if dests:
             for d in dests:
                 if d in ("RZ", "URZ", "PT", "UPT"):
                     continue
                 val = new
-                if guard_t == SEC:
-                    val = SEC
+                if d.lstrip("U").startswith("P"):
+                    val = SEC if is_sec(val) else val        # a predicate is one bit
+                if is_sec(guard_t):
+                    li2 = lop3_imm()
+                    if li2 is not None and li2[2] == 0xFC and not d.lstrip("U").startswith("P"):
+                        val = (val if is_sec(val) else 0) | li2[1]   # @secret R |= imm: only the imm bits become secret
+                    else:
+                        val = SEC
                 if ins.guard and ins.guard not in ("PT", "UPT"):
                     # a predicated write keeps the old value on the other path ... unless the
                     # complementary write (@P / @!P of the same, unmodified predicate) came just before
                     pend = st.get(("pend", d))
                     if pend and pend[0] == ins.guard and pend[1] != ins.neg:
-                        val = SEC if SEC in (pend[2], val) else (val or pend[2])
+                        val = tjoin(pend[2], val)
                         st.pop(("pend", d), None)
                     else:
                         old = st.get(d)
                         st[("pend", d)] = (ins.guard, ins.neg, val)
-                        val = SEC if SEC in (old, val) else (val or old)
+                        val = tjoin(old, val)
                 else:
                     st.pop(("pend", d), None)
                 if val is None:
@@ -448,13 +493,13 @@ def audit(name, insns, secret_offsets, verbose=False):
             raise RuntimeError("taint analysis did not converge")
 
     secret_loads = sum(1 for k, ins in enumerate(insns) if ins.op.startswith(("LDG", "LD.")) and state[k] is not None and
-                       any(state[k].get(r) in (PTR, SEC) for r in classify(ins)[2]))
+                       any(state[k].get(r) is not None for r in classify(ins)[2]))
     tainted_instrs = 0
     for k, ins in enumerate(insns):
         if state[k] is None:
             continue
         d, s, a, dd = classify(ins)
-        if any(state[k].get(r) == SEC for r in s + dd):
+        if any(is_sec(state[k].get(r)) for r in s + dd):
             tainted_instrs += 1
     if os.environ.get("CT_EXPLAIN"):
         want = int(os.environ["CT_EXPLAIN"], 16)
@@ -470,7 +515,7 @@ def audit(name, insns, secret_offsets, verbose=False):
                     print("  " * depth + f"{hex(insns[j].addr)}: {insns[j].text}    tainted-in: {tag}")
                     if depth < 6:
                         for r, v in tag.items():
-                            if v == SEC and (j, r) not in seen:
+                            if is_sec(v) and (j, r) not in seen:
                                 seen.add((j, r))
                                 explain(j, r, depth + 1)
                     return
@@ -478,7 +523,7 @@ def audit(name, insns, secret_offsets, verbose=False):
             d, s_, a_, dd = classify(insns[k0])
             print("EXPLAIN", name, hex(want), insns[k0].text)
             for r in s_ + a_ + ([insns[k0].guard] if insns[k0].guard else []):
-                if state[k0].get(r) == SEC:
+                if is_sec(state[k0].get(r)):
                     explain(k0, r, 1)
     return {"kernel": name, "instructions": n, "secret_loads": secret_loads, "instructions_on_secret_data": tainted_instrs,
             "stack_holds_secrets": stack_secret[0], "reached": sum(1 for s in state if s is not None),
