@@ -34,10 +34,16 @@
 #else
 #define EDG_POW_INLINE EDG_NOINLINE
 #endif
+#if defined(EDG_FE_NOINLINE)
+#define EDG_FE_MUL static __host__ __device__ __noinline__     /* experiment: out-of-line multiply / square (I-cache footprint) */
+#else
+#define EDG_FE_MUL EDG_HD
+#endif
 #else
 #define EDG_HD static inline
 #define EDG_NOINLINE static
 #define EDG_POW_INLINE static
+#define EDG_FE_MUL static inline
 #endif
 
 namespace edg {
@@ -247,7 +253,7 @@ EDG_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
 EDG_HD void fe_carry(fe &r, const fe &a) { fe_copy(r, a); }                   // kept for the point formulas' sake: nothing to carry
 
 // r = a * b mod p.  72 IMAD.WIDE.U32.                            [reference: fld_mul, fld.c:210 / :448]
-EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
+EDG_FE_MUL void fe_mul(fe &r, const fe &a, const fe &b) {
     EDG_COUNT_MUL();
     u32 w[17];
 #if defined(__CUDA_ARCH__)
@@ -274,7 +280,7 @@ EDG_HD void fe_mul(fe &r, const fe &a, const fe &b) {
 
 // r = a^2 mod p.  44 IMAD.WIDE.U32 (28 cross products, doubled by a 1-bit shift, + 8 squares + 8 fold).
 //                                                                  [reference: fld_sq, fld.c:250 / :503]
-EDG_HD void fe_sq(fe &r, const fe &a) {
+EDG_FE_MUL void fe_sq(fe &r, const fe &a) {
     EDG_COUNT_SQ();
     u32 w[17];
 #if defined(__CUDA_ARCH__)

@@ -37,6 +37,13 @@ __device__ __forceinline__ void msg_of(const uint8_t *&m, u64 &len, const uint8_
     else { m = msgs + (size_t)i * fixed_len; len = fixed_len; }
 }
 
+// Overwrite per-thread scratch that held secret-derived values (the GPU analogue of the reference's
+// burnstack(), lib/burnstack.c:12-19); volatile so the stores are not optimised away.
+__device__ __forceinline__ void scrub(fe *p, int count) {
+    volatile u32 *w = reinterpret_cast<volatile u32 *>(p);
+    for (int i = 0; i < count * 8; i++) w[i] = 0;
+}
+
 // grid = min(blocks needed, SMs x resident blocks per SM): persistent blocks, grid-stride inside.
 template <typename K>
 int grid_for(K kernel, size_t n, int smem, int sm_count, int *blocks_per_sm_out) {

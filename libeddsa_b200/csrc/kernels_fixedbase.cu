@@ -24,21 +24,57 @@ constexpr int kCombBytes = EDG_BASE_COMB_WORDS * 4;      // 49 152
 __global__ void __launch_bounds__(kThreads, EDG_LB_X25519_BASE) k_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        u32 s[8], o[8];
-        load8(s, scalar, i);
-        x25519_base_op(o, s, s_comb);
-        store8(out, i, o);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+        fe N[EDG_BATCH], D[EDG_BATCH];
+        int cnt = 0;
+#pragma unroll 1
+        for (int k = 0; k < EDG_BATCH; k++) {
+            const size_t i = i0 + (size_t)k * T;
+            if (i >= n) break;
+            u32 s[8];
+            load8(s, scalar, i);
+            x25519_base_front(N[k], D[k], s, s_comb);
+            cnt++;
+        }
+        fe_batch_inv(D, cnt);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            u32 o[8];
+            x25519_back(o, N[k], D[k]);
+            store8(out, i0 + (size_t)k * T, o);
+        }
+        scrub(N, EDG_BATCH);
+        scrub(D, EDG_BATCH);
     }
 }
 
 __global__ void __launch_bounds__(kThreads, EDG_LB_GENPUB) k_genpub(size_t n, uint8_t *pub, const uint8_t *sec) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        u32 o[8];
-        ed25519_genpub_op(o, sec + 32 * i, s_comb);
-        store8(pub, i, o);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH];
+        int cnt = 0;
+#pragma unroll 1
+        for (int k = 0; k < EDG_BATCH; k++) {
+            const size_t i = i0 + (size_t)k * T;
+            if (i >= n) break;
+            ge_p3 A;
+            ed25519_genpub_front(A, sec + 32 * i, s_comb);
+            fe_copy(X[k], A.X); fe_copy(Y[k], A.Y); fe_copy(Z[k], A.Z);
+            cnt++;
+        }
+        fe_batch_inv(Z, cnt);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            u32 o[8];
+            ge_tobytes_zinv(o, X[k], Y[k], Z[k]);
+            store8(pub, i0 + (size_t)k * T, o);
+        }
+        scrub(X, EDG_BATCH);
+        scrub(Y, EDG_BATCH);
+        scrub(Z, EDG_BATCH);
     }
 }
 
@@ -46,14 +82,37 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_
                                                    const unsigned long long *off, unsigned long long fixed_len) {
     extern __shared__ __align__(16) u32 s_comb[];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        u32 p[8], o[16];
-        const uint8_t *m; u64 len;
-        msg_of(m, len, msgs, off, fixed_len, i);
-        load8(p, pub, i);
-        ed25519_sign_op(o, sec + 32 * i, p, m, len, s_comb);
-        store8(sig, 2 * i, o);
-        store8(sig, 2 * i + 1, o + 8);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH], AR[2 * EDG_BATCH];     // AR: secret scalar a and nonce r of each signature
+        int cnt = 0;
+#pragma unroll 1
+        for (int k = 0; k < EDG_BATCH; k++) {
+            const size_t i = i0 + (size_t)k * T;
+            if (i >= n) break;
+            const uint8_t *m; u64 len;
+            msg_of(m, len, msgs, off, fixed_len, i);
+            ge_p3 R;
+            ed25519_sign_front(AR[2 * k].v, AR[2 * k + 1].v, R, sec + 32 * i, m, len, s_comb);
+            fe_copy(X[k], R.X); fe_copy(Y[k], R.Y); fe_copy(Z[k], R.Z);
+            cnt++;
+        }
+        fe_batch_inv(Z, cnt);
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {
+            const size_t i = i0 + (size_t)k * T;
+            u32 p[8], o[16];
+            const uint8_t *m; u64 len;
+            msg_of(m, len, msgs, off, fixed_len, i);
+            load8(p, pub, i);
+            ed25519_sign_back(o, AR[2 * k].v, AR[2 * k + 1].v, X[k], Y[k], Z[k], p, m, len);
+            store8(sig, 2 * i, o);
+            store8(sig, 2 * i + 1, o + 8);
+        }
+        scrub(X, EDG_BATCH);
+        scrub(Y, EDG_BATCH);
+        scrub(Z, EDG_BATCH);
+        scrub(AR, 2 * EDG_BATCH);
     }
 }
 

@@ -19,11 +19,30 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify(size_t n, ui
     __shared__ __align__(16) u32 s_small[EDG_BASE_SMALL_WORDS + 2];
     stage_table(s_small, BASE_SMALL, EDG_BASE_SMALL_WORDS);
     u32 *qtab = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EDG_QTAB_WORDS;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const uint8_t *m; u64 len;
-        msg_of(m, len, msgs, off, fixed_len, i);
-        ok[i] = (uint8_t)ed25519_verify_op(reinterpret_cast<const u32 *>(sig + 64 * i), reinterpret_cast<const u32 *>(pub + 32 * i),
-                                           m, len, qtab, s_small);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH];
+        u32 on_curve = 0;                                      // bit k: public key of the k-th signature decoded to a curve point
+        int cnt = 0;
+#pragma unroll 1
+        for (int k = 0; k < EDG_BATCH; k++) {                 // phase 1: C = S*B + t*(-A), projective
+            const size_t i = i0 + (size_t)k * T;
+            if (i >= n) break;
+            const uint8_t *m; u64 len;
+            msg_of(m, len, msgs, off, fixed_len, i);
+            ge_p3 R;
+            const u32 oc = ed25519_verify_front(R, reinterpret_cast<const u32 *>(sig + 64 * i), reinterpret_cast<const u32 *>(pub + 32 * i),
+                                                m, len, qtab, s_small);
+            on_curve |= (oc & 1u) << k;
+            fe_copy(X[k], R.X); fe_copy(Y[k], R.Y); fe_copy(Z[k], R.Z);
+            cnt++;
+        }
+        fe_batch_inv(Z, cnt);                                  // phase 2: one inversion per batch
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {                        // phase 3: encode and compare with the signature's R bytes
+            const size_t i = i0 + (size_t)k * T;
+            ok[i] = (uint8_t)ed25519_verify_back(X[k], Y[k], Z[k], (on_curve >> k) & 1u, reinterpret_cast<const u32 *>(sig + 64 * i));
+        }
     }
 }
 

@@ -10,12 +10,29 @@ using namespace edg;
 namespace {
 
 __global__ void __launch_bounds__(kThreads, EDG_LB_X25519) k_x25519(size_t n, uint8_t *out, const uint8_t *scalar, const uint8_t *point) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        u32 s[8], p[8], o[8];
-        load8(s, scalar, i);
-        load8(p, point, i);
-        x25519_op(o, s, p);
-        store8(out, i, o);
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+        fe X[EDG_BATCH], Z[EDG_BATCH];
+        int cnt = 0;
+#pragma unroll 1
+        for (int k = 0; k < EDG_BATCH; k++) {                 // phase 1: ladders
+            const size_t i = i0 + (size_t)k * T;
+            if (i >= n) break;
+            u32 s[8], p[8];
+            load8(s, scalar, i);
+            load8(p, point, i);
+            x25519_front(X[k], Z[k], s, p);
+            cnt++;
+        }
+        fe_batch_inv(Z, cnt);                                  // phase 2: one inversion for the whole batch
+#pragma unroll 1
+        for (int k = 0; k < cnt; k++) {                        // phase 3: X / Z, canonical bytes
+            u32 o[8];
+            x25519_back(o, X[k], Z[k]);
+            store8(out, i0 + (size_t)k * T, o);
+        }
+        scrub(X, EDG_BATCH);
+        scrub(Z, EDG_BATCH);
     }
 }
 

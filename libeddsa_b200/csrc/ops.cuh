@@ -15,19 +15,55 @@
 
 namespace edg {
 
+// Every operation ends with one field inversion (254 S + 11 M: 27 % of a fixed-base operation, 8 % of
+// an X25519, 6 % of a verify).  The kernels therefore run each thread over up to EDG_BATCH operations
+// in three phases — *_front (everything up to the projective result), ONE shared inversion for the
+// thread's whole batch (Montgomery's trick: 3 multiplications per element), *_back (encode / hash /
+// compare) — which removes 7/8 of the inversions.  The single-operation functions below (used by the
+// host-side unit tests) are front + fe_inv + back, so both paths execute the same code.
+#define EDG_BATCH 8
+
+// z[0..cnt) <- their inverses, sharing one exponentiation; a zero stays zero (inv(0) = 0) and
+// does not disturb its neighbours.  Branch-free in the data (cnt is public).   [fld_inv, fld.c:579]
+EDG_HD void fe_batch_inv(fe *z, int cnt) {
+    fe pre[EDG_BATCH], acc, one;
+    fe_set_u32(one, 1);
+    fe_set_u32(acc, 1);
+#pragma unroll 1
+    for (int k = 0; k < cnt; k++) {
+        const u32 zero = ct_mask(0u - fe_is_zero(z[k]));
+        fe zk;
+        fe_select(zk, z[k], one, zero);                   // 0 -> 1 so the running product stays invertible
+        fe_copy(pre[k], acc);
+        fe_mul(acc, acc, zk);
+    }
+    fe_inv(acc, acc);
+#pragma unroll 1
+    for (int k = cnt - 1; k >= 0; k--) {
+        const u32 zero = ct_mask(0u - fe_is_zero(z[k]));
+        fe zk, t, zz;
+        fe_select(zk, z[k], one, zero);
+        fe_mul(t, acc, pre[k]);                           // 1 / z_k
+        fe_mul(acc, acc, zk);                             // 1 / (z_0 .. z_{k-1})
+        fe_set_u32(zz, 0);
+        fe_select(z[k], t, zz, zero);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // X25519 variable base: Montgomery ladder.              [do_x25519 x25519.c:129-150, mg_scale :104-123,
 //                                                         montgomery :60-94, ctmemswap :36-49]
 // Constant time: the scalar only ever feeds swap masks.
 // ------------------------------------------------------------------------------------------------
-EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
+// front: (x2 : z2) = clamp(scalar) * (u : 1)
+EDG_HD void x25519_front(fe &x2, fe &z2, const u32 scalar[8], const u32 point[8]) {
     u32 e[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) e[i] = scalar[i];
     e[0] &= 0xfffffff8u;                                  // x25519.c:138-140
     e[7] &= 0x7fffffffu;
     e[7] |= 0x40000000u;
-    fe x1, x2, z2, x3, z3;
+    fe x1, x3, z3;
     fe_from_words(x1, point);                             // all 256 bits, bit 255 -> +19 (Q6)   x25519.c:142
     fe_set_u32(x2, 1); fe_set_u32(z2, 0);                 // (1 : 0)                              x25519.c:111-112
     fe_copy(x3, x1); fe_set_u32(z3, 1);                   // (u : 1)
@@ -63,9 +99,20 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
         fe_cswap(x2, x3, mask);
         fe_cswap(z2, z3, mask);
     }
-    fe_inv(z2, z2);                                       // inv(0) = 0 (Q7)                     x25519.c:147
-    fe_mul(x2, x2, z2);
-    fe_to_words(out, x2);
+}
+
+// back: out = x2 * zinv, canonical bytes                                                          x25519.c:147-149
+EDG_HD void x25519_back(u32 out[8], const fe &x2, const fe &zinv) {
+    fe t;
+    fe_mul(t, x2, zinv);
+    fe_to_words(out, t);
+}
+
+EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
+    fe x2, z2;
+    x25519_front(x2, z2, scalar, point);
+    fe_inv(z2, z2);                                       // inv(0) = 0 (Q7)
+    x25519_back(out, x2, z2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -110,28 +157,48 @@ EDG_HD void ed25519_expand_key(u32 a[8], u64 prefix[4], const uint8_t *sk) {
 }
 
 // pub = encode(a * B)                                                 [genpub, ed25519-sha512.c:53-67]
-EDG_HD void ed25519_genpub_op(u32 pub[8], const uint8_t *sk, const u32 *comb) {
+EDG_HD void ed25519_genpub_front(ge_p3 &A, const uint8_t *sk, const u32 *comb) {
     u32 a[8];
     u64 prefix[4];
     ed25519_expand_key(a, prefix, sk);
-    ge_p3 A;
     ge_scalarmult_base_ct(A, a, comb);
-    ge_tobytes(pub, A);
+}
+
+// encode (X * zinv, Y * zinv)                                        [ed_export, ed.c:155-169]
+EDG_HD void ge_tobytes_zinv(u32 out[8], const fe &X, const fe &Y, const fe &zinv) {
+    fe x, y;
+    fe_mul(x, X, zinv);
+    fe_mul(y, Y, zinv);
+    ge_affine_tobytes(out, x, y);
+}
+
+EDG_HD void ed25519_genpub_op(u32 pub[8], const uint8_t *sk, const u32 *comb) {
+    ge_p3 A;
+    ed25519_genpub_front(A, sk, comb);
+    fe_inv(A.Z, A.Z);
+    ge_tobytes_zinv(pub, A.X, A.Y, A.Z);
 }
 
 // sig = (R, S)                                                        [sign, ed25519-sha512.c:84-123]
-EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], const uint8_t *msg, u64 len, const u32 *comb) {
-    u32 a[8], r[8], t[8], h[16];
-    u64 pre[8], st[8];
+// front: secret scalar a, nonce r = H(prefix || M) mod L and the point R = r B (projective)
+EDG_HD void ed25519_sign_front(u32 a[8], u32 r[8], ge_p3 &R, const uint8_t *sk, const uint8_t *msg, u64 len, const u32 *comb) {
+    u32 h[16];
+    u64 pre[4], st[8];
     ed25519_expand_key(a, pre, sk);
     sha512_prefixed<4>(st, pre, msg, len);                // r = H(prefix || M)        :101-105
     sha512_state_to_le_words(h, st);
     sc_reduce512(r, h);
-    ge_p3 R;
     ge_scalarmult_base_ct(R, r, comb);                    // R = r B                   :108-109
-    ge_tobytes(sig, R);
+}
+
+// back: encode R, t = H(R || pub || M) mod L with pub as given (Q8), S = r + t a mod L
+EDG_HD void ed25519_sign_back(u32 sig[16], const u32 a[8], const u32 r[8], const fe &X, const fe &Y, const fe &zinv,
+                              const u32 pub[8], const uint8_t *msg, u64 len) {
+    u32 t[8], h[16];
+    u64 pre[8], st[8];
+    ge_tobytes_zinv(sig, X, Y, zinv);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {                          // t = H(R || pub || M)       :112-117, pub as given (Q8)
+    for (int k = 0; k < 4; k++) {                          // :112-117
         pre[k] = be64_from_le_words(sig[2 * k], sig[2 * k + 1]);
         pre[4 + k] = be64_from_le_words(pub[2 * k], pub[2 * k + 1]);
     }
@@ -141,8 +208,17 @@ EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], co
     sc_muladd(sig + 8, t, a, r);                          // S = r + t a mod L         :120-122
 }
 
+EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], const uint8_t *msg, u64 len, const u32 *comb) {
+    u32 a[8], r[8];
+    ge_p3 R;
+    ed25519_sign_front(a, r, R, sk, msg, len, comb);
+    fe_inv(R.Z, R.Z);
+    ed25519_sign_back(sig, a, r, R.X, R.Y, R.Z, pub, msg, len);
+}
+
 // out = u-coordinate of (clamp(scalar) mod L) * B                     [do_x25519_base, x25519.c:158-197]
-EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
+// front: num = Z + Y, den = Z - Y of the Edwards point; back: u = num / den
+EDG_HD void x25519_base_front(fe &num, fe &den, const u32 scalar[8], const u32 *comb) {
     u32 e[8], x[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) e[i] = scalar[i];
@@ -150,12 +226,15 @@ EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
     sc_reduce256(x, e);                                   // Q9
     ge_p3 R;
     ge_scalarmult_base_ct(R, x, comb);
-    fe u, t;
-    fe_sub(t, R.Z, R.Y);                                  // x25519.c:190-194
-    fe_inv(t, t);
-    fe_add(u, R.Z, R.Y);
-    fe_mul(u, u, t);
-    fe_to_words(out, u);
+    fe_sub(den, R.Z, R.Y);                                // x25519.c:190-194
+    fe_add(num, R.Z, R.Y);
+}
+
+EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
+    fe num, den;
+    x25519_base_front(num, den, scalar, comb);
+    fe_inv(den, den);
+    x25519_back(out, num, den);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -178,7 +257,8 @@ EDG_HD void load_words8(u32 w[8], const u32 *src) {
 
 // sig / pub point at this signature's 64 / 32 bytes (16-byte aligned); they are re-read where
 // needed instead of being kept live in registers across the scalar-multiplication loop.
-EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
+// front: C = S*B + t*(-A) in projective form; returns the on-curve mask of A
+EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
     u32 et[8], es[8];
     {
         // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
@@ -220,7 +300,6 @@ EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg,
         }
     }
 
-    ge_p3 R;
     ge_identity(R);
 #pragma unroll 1
     for (int j = 63; j >= 0; j--) {
@@ -247,13 +326,25 @@ EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg,
             ge_madd(R, R, b, false);
         }
     }
+    return on_curve;
+}
+
+// back: accept iff encode(C) equals the first 32 signature bytes (Q2) and A was on the curve (Q5 policy)   :177-180
+EDG_HD u32 ed25519_verify_back(const fe &X, const fe &Y, const fe &zinv, u32 on_curve, const u32 *sig) {
     u32 check[8], r8[8];
-    ge_tobytes(check, R);                                 // :177
+    ge_tobytes_zinv(check, X, Y, zinv);
     load_words8(r8, sig);
     u32 diff = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) diff |= check[i] ^ r8[i];    // encode(C) == R bytes (Q2)            :180
-    return (diff == 0 ? 1u : 0u) & (on_curve & 1u);       // off-curve A -> reject (Q5 policy)
+    for (int i = 0; i < 8; i++) diff |= check[i] ^ r8[i];
+    return (diff == 0 ? 1u : 0u) & (on_curve & 1u);
+}
+
+EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
+    ge_p3 R;
+    const u32 on_curve = ed25519_verify_front(R, sig, pub, msg, len, qtab, small);
+    fe_inv(R.Z, R.Z);
+    return ed25519_verify_back(R.X, R.Y, R.Z, on_curve, sig);
 }
 
 // pk_ed25519_to_x25519: u = (1 + y) / (1 - y) of the decoded point.   [ed25519-sha512.c:187-237]

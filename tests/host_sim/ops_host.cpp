@@ -25,5 +25,10 @@ int hs_verify(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64
 void hs_x25519_base(uint8_t *out, const uint8_t *scalar) { u32 o[8], s[8]; memcpy(s, scalar, 32); x25519_base_op(o, s, BASE_COMB); memcpy(out, o, 32); }
 void hs_pk_conv(uint8_t *out, const uint8_t *in) { u32 o[8], p[8]; memcpy(p, in, 32); pk_ed25519_to_x25519_op(o, p); memcpy(out, o, 32); }
 void hs_sk_conv(uint8_t *out, const uint8_t *in) { u32 o[8]; sk_ed25519_to_x25519_op(o, in); memcpy(out, o, 32); }
+void hs_batch_inv(uint8_t *z, int cnt) {   // z: cnt x 32 bytes, in place
+    fe t[EDG_BATCH]; for (int k = 0; k < cnt; k++) memcpy(t[k].v, z + 32 * k, 32);
+    fe_batch_inv(t, cnt);
+    for (int k = 0; k < cnt; k++) { u32 w[8]; fe_to_words(w, t[k]); memcpy(z + 32 * k, w, 32); }
+}
 void hs_counts(unsigned long *mul, unsigned long *sq, int reset) { *mul = edg_cnt_mul; *sq = edg_cnt_sq; if (reset) edg_cnt_mul = edg_cnt_sq = 0; }
 }
