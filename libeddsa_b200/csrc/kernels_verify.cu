@@ -10,7 +10,8 @@ using namespace edg;
 #include "base_table.inc"
 
 #ifndef EDG_LB_VERIFY
-#define EDG_LB_VERIFY 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#define EDG_LB_VERIFY 4     /* min resident blocks per SM the register allocator must allow: 128 registers, 4 warps/SMSP
+                               (measured +4 % over 3 blocks, profiles/r01_summary.md) */
 #endif
 namespace {
 

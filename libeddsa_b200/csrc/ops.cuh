@@ -300,6 +300,11 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
         }
     }
 
+    // Straus main loop.  Each window is six steps through ONE loop body — four doublings, the addition of
+    // the (-A)-table entry, the addition of the B-table entry — because doubling and addition end in the
+    // same four products (X3 = E F, Y3 = G H, Z3 = F G, T3 = E H): sharing that tail halves the loop's
+    // instruction footprint (the fully inlined form overflowed the instruction cache: 1.1 stall cycles per
+    // issue with reason no_instruction, profiles/r01_summary.md).  T3 is only computed when an addition follows.
     ge_identity(R);
 #pragma unroll 1
     for (int j = 63; j >= 0; j--) {
@@ -308,22 +313,51 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
 #pragma unroll
         for (int i = 7; i > 0; i--) { et[i] = (et[i] << 4) | (et[i - 1] >> 28); es[i] = (es[i] << 4) | (es[i - 1] >> 28); }
         et[0] <<= 4; es[0] <<= 4;
-        if (j != 63) {
 #pragma unroll 1
-            for (int k = 0; k < 4; k++) ge_dbl(R, R, k == 3);
-        }
-        {
-            const u32 neg = (u32)(dt >> 31);
-            const u32 absd = ((u32)dt ^ neg) - neg;
-            ge_cached c;
-            ge_cached_load(c, qtab + 32 * absd);
-            ge_cached_cneg(c, neg);
-            ge_add_cached(R, R, c, true);
-        }
-        {
-            ge_pre b;
-            ge_pre_load(b, small, ds);
-            ge_madd(R, R, b, false);
+        for (int step = (j == 63 ? 4 : 0); step < 6; step++) {
+            fe e, f, g, h;
+            if (step < 4) {                                   // doubling prologue                 [ed_double, ed.c:211]
+                fe a, b, c, s;
+                fe_sq(a, R.X);
+                fe_sq(b, R.Y);
+                fe_sq(c, R.Z);
+                fe_dbl(c, c);
+                fe_add(s, R.X, R.Y);
+                fe_sq(s, s);
+                fe_add(h, a, b);
+                fe_sub(e, h, s);
+                fe_sub(g, a, b);
+                fe_add(f, c, g);
+            } else {                                          // addition prologue                 [ed_add ed.c:175 / ed_add_pc :282]
+                fe ypx, ymx, t2d, a, b, c, d;
+                if (step == 4) {                              // dt * (-A): cached entry from this thread's scratch
+                    const u32 neg = (u32)(dt >> 31);
+                    const u32 absd = ((u32)dt ^ neg) - neg;
+                    ge_cached q;
+                    ge_cached_load(q, qtab + 32 * absd);
+                    ge_cached_cneg(q, neg);
+                    fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.t2d);
+                    fe_mul(d, R.Z, q.z2);
+                } else {                                      // ds * B: affine entry from shared memory (Z2 = 1)
+                    ge_pre q;
+                    ge_pre_load(q, small, ds);
+                    fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.xy2d);
+                    fe_dbl(d, R.Z);
+                }
+                fe_sub(a, R.Y, R.X);
+                fe_mul(a, a, ymx);
+                fe_add(b, R.Y, R.X);
+                fe_mul(b, b, ypx);
+                fe_mul(c, R.T, t2d);
+                fe_sub(e, b, a);
+                fe_sub(f, d, c);
+                fe_add(g, d, c);
+                fe_add(h, b, a);
+            }
+            fe_mul(R.X, e, f);                                // shared tail
+            fe_mul(R.Y, g, h);
+            fe_mul(R.Z, f, g);
+            if (step == 3 || step == 4) fe_mul(R.T, e, h);
         }
     }
     return on_curve;
