@@ -157,6 +157,32 @@ template <> __device__ __forceinline__ void cmad<4>(u32 *acc, const u32 *a, u32 
         : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
 }
 
+// Same rows WITHOUT the carry-out word: for use when the top 64-bit slot of the row is "fresh" (it holds
+// at most the 0/1 carry caught from an earlier row), because then  a*b + slot + carry-in
+// <= (2^32-1)^2 + 2 < 2^64  cannot overflow.  Saves the catch instruction and the zero word of the pair.
+template <int CNT> __device__ __forceinline__ void cmadf(u32 *acc, const u32 *a, u32 bi);
+template <> __device__ __forceinline__ void cmadf<0>(u32 *, const u32 *, u32) {}
+template <> __device__ __forceinline__ void cmadf<1>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.u32 %1, %2, %3, %1;"
+        : "+r"(acc[0]), "+r"(acc[1]) : "r"(a[0]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmadf<2>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %4, %6, %0; madc.hi.cc.u32 %1, %4, %6, %1; madc.lo.cc.u32 %2, %5, %6, %2; madc.hi.u32 %3, %5, %6, %3;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]) : "r"(a[0]), "r"(a[2]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmadf<3>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %6, %9, %0; madc.hi.cc.u32 %1, %6, %9, %1; madc.lo.cc.u32 %2, %7, %9, %2; madc.hi.cc.u32 %3, %7, %9, %3; "
+        "madc.lo.cc.u32 %4, %8, %9, %4; madc.hi.u32 %5, %8, %9, %5;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(bi));
+}
+template <> __device__ __forceinline__ void cmadf<4>(u32 *acc, const u32 *a, u32 bi) {
+    asm("mad.lo.cc.u32 %0, %8, %12, %0; madc.hi.cc.u32 %1, %8, %12, %1; madc.lo.cc.u32 %2, %9, %12, %2; madc.hi.cc.u32 %3, %9, %12, %3; "
+        "madc.lo.cc.u32 %4, %10, %12, %4; madc.hi.cc.u32 %5, %10, %12, %5; madc.lo.cc.u32 %6, %11, %12, %6; madc.hi.u32 %7, %11, %12, %7;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7])
+        : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+}
+
 // w[1..15] += od[0..14]: merge of the odd-word accumulator, one carry chain
 __device__ __forceinline__ void merge_odd(u32 *w, const u32 *od) {
     asm("add.cc.u32 %0, %0, %15; addc.cc.u32 %1, %1, %16; addc.cc.u32 %2, %2, %17; addc.cc.u32 %3, %3, %18; addc.cc.u32 %4, %4, %19; "
@@ -205,18 +231,77 @@ static inline u32 subw8(u32 r[8], u32 x) {
 #endif
 
 // w (16 words, < 2^512) -> r = lo + 38 hi, weakly reduced.  8 wide multiplies.
-EDG_HD void fe_fold512(fe &r, const u32 w[16]) {
-    u64 c = 0;
+#if defined(__CUDA_ARCH__)
+// Device forms.  The eight products 38 * hi_j ride hardware carry chains straight into the low half — no
+// 64-bit temporaries — and every chain works on the (even, odd) register pairs its accumulator already
+// lives in, so ptxas never has to re-pair registers with moves.
+
+// last step shared by both: w[0..7] + 38 * t8 (t8 <= 40) -> r; if that wraps past 2^256 the wrapped value is
+// tiny, so the final +38 cannot carry again
+__device__ __forceinline__ void fe_fold_tail(fe &r, u32 *w, u32 t8) {
+    const u32 c2 = addw8(w, t8 * 38u);
+    r.v[0] = w[0] + (38u & (0u - c2));
 #pragma unroll
+    for (int j = 1; j < 8; j++) r.v[j] = w[j];
+}
+
+// words 0..7 += 38 * (even words of the high half); returns the carry out
+__device__ __forceinline__ u32 fe_fold_even(u32 *w) {
+    u32 t8;
+    asm("mad.lo.cc.u32 %0, %9, 38, %0; madc.hi.cc.u32 %1, %9, 38, %1; madc.lo.cc.u32 %2, %10, 38, %2; madc.hi.cc.u32 %3, %10, 38, %3; "
+        "madc.lo.cc.u32 %4, %11, 38, %4; madc.hi.cc.u32 %5, %11, 38, %5; madc.lo.cc.u32 %6, %12, 38, %6; madc.hi.cc.u32 %7, %12, 38, %7; "
+        "addc.u32 %8, 0, 0;"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "=r"(t8)
+        : "r"(w[8]), "r"(w[10]), "r"(w[12]), "r"(w[14]));
+    return t8;
+}
+
+// Multiplication: even-word accumulator w[0..15], odd-word accumulator od[0..14] (od[k] = word k + 1), not yet merged.
+__device__ __forceinline__ void fe_fold_mul(fe &r, u32 *w, u32 *od) {
+    // high half first: words 8..15 += od[7..14] (the product is < 2^512: no carry out)
+    asm("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11; "
+        "addc.cc.u32 %4, %4, %12; addc.cc.u32 %5, %5, %13; addc.cc.u32 %6, %6, %14; addc.u32 %7, %7, %15;"
+        : "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]), "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "r"(od[7]), "r"(od[8]), "r"(od[9]), "r"(od[10]), "r"(od[11]), "r"(od[12]), "r"(od[13]), "r"(od[14]));
+    u32 t8 = fe_fold_even(w);
+    // odd words of the high half fold onto words 1, 3, 5, 7 = the pairs (od0, od1) .. (od6, x); x <= 37 + 1
+    u32 x = 0;
+    asm("mad.lo.cc.u32 %0, %8, 38, %0; madc.hi.cc.u32 %1, %8, 38, %1; madc.lo.cc.u32 %2, %9, 38, %2; madc.hi.cc.u32 %3, %9, 38, %3; "
+        "madc.lo.cc.u32 %4, %10, 38, %4; madc.hi.cc.u32 %5, %10, 38, %5; madc.lo.cc.u32 %6, %11, 38, %6; madc.hi.u32 %7, %11, 38, %7;"
+        : "+r"(od[0]), "+r"(od[1]), "+r"(od[2]), "+r"(od[3]), "+r"(od[4]), "+r"(od[5]), "+r"(od[6]), "+r"(x)
+        : "r"(w[9]), "r"(w[11]), "r"(w[13]), "r"(w[15]));
+    // low half: words 1..7 += od[0..6]; word 8 = t8 + x + carry <= 1 + 38 + 1
+    asm("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11; "
+        "addc.cc.u32 %4, %4, %12; addc.cc.u32 %5, %5, %13; addc.cc.u32 %6, %6, %14; addc.u32 %7, %7, %15;"
+        : "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(t8)
+        : "r"(od[0]), "r"(od[1]), "r"(od[2]), "r"(od[3]), "r"(od[4]), "r"(od[5]), "r"(od[6]), "r"(x));
+    fe_fold_tail(r, w, t8);
+}
+
+// Squaring: one merged 16-word value w.  The odd high words are multiplied without a chain (their register
+// pairs would be misaligned against w) and added in with one carry chain.
+__device__ __forceinline__ void fe_fold_sq(fe &r, u32 *w) {
+    u32 t8 = fe_fold_even(w);
+    const u64 q0 = mulw(w[9], 38u), q1 = mulw(w[11], 38u), q2 = mulw(w[13], 38u), q3 = mulw(w[15], 38u);
+    asm("add.cc.u32 %0, %0, %8; addc.cc.u32 %1, %1, %9; addc.cc.u32 %2, %2, %10; addc.cc.u32 %3, %3, %11; "
+        "addc.cc.u32 %4, %4, %12; addc.cc.u32 %5, %5, %13; addc.cc.u32 %6, %6, %14; addc.u32 %7, %7, %15;"
+        : "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(t8)
+        : "r"((u32)q0), "r"((u32)(q0 >> 32)), "r"((u32)q1), "r"((u32)(q1 >> 32)), "r"((u32)q2), "r"((u32)(q2 >> 32)),
+          "r"((u32)q3), "r"((u32)(q3 >> 32)));
+    fe_fold_tail(r, w, t8);
+}
+#else
+static inline void fe_fold512(fe &r, const u32 w[17]) {
+    u64 c = 0;
     for (int j = 0; j < 8; j++) {
         const u64 t = mulw(w[8 + j], 38u) + w[j] + c;
         r.v[j] = (u32)t;
         c = t >> 32;
     }
-    // c <= 38: fold it once more; if that wraps past 2^256 the wrapped value is tiny, so +38 cannot carry again
     const u32 c2 = addw8(r.v, (u32)c * 38u);
     r.v[0] += 38u & (0u - c2);
 }
+#endif
 
 // r = a + b                                            [reference: fld_add, fld.h:94]
 EDG_HD void fe_add(fe &r, const fe &a, const fe &b) {
@@ -261,12 +346,18 @@ EDG_FE_MUL void fe_mul(fe &r, const fe &a, const fe &b) {
     u32 od[17];
 #pragma unroll
     for (int i = 0; i < 17; i++) w[i] = od[i] = 0;
+    // Rows whose top slot is fresh (first row at that offset of its accumulator) cannot carry out: cmadf.
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        if ((i & 1) == 0) { cmad<4>(w + i, a.v, b.v[i]); cmad<4>(od + i, a.v + 1, b.v[i]); }
-        else              { cmad<4>(w + i + 1, a.v + 1, b.v[i]); cmad<4>(od + i - 1, a.v, b.v[i]); }
+        if ((i & 1) == 0) {
+            if (i == 0) cmadf<4>(w + i, a.v, b.v[i]); else cmad<4>(w + i, a.v, b.v[i]);
+            cmadf<4>(od + i, a.v + 1, b.v[i]);
+        } else {
+            cmadf<4>(w + i + 1, a.v + 1, b.v[i]);
+            cmad<4>(od + i - 1, a.v, b.v[i]);
+        }
     }
-    merge_odd(w, od);
+    fe_fold_mul(r, w, od);
 #else
     for (int i = 0; i < 17; i++) w[i] = 0;
     for (int i = 0; i < 8; i++) {
@@ -274,8 +365,8 @@ EDG_FE_MUL void fe_mul(fe &r, const fe &a, const fe &b) {
         for (int j = 0; j < 8; j++) { const u64 t = mulw(a.v[j], b.v[i]) + w[i + j] + c; w[i + j] = (u32)t; c = t >> 32; }
         w[i + 8] = (u32)c;
     }
-#endif
     fe_fold512(r, w);
+#endif
 }
 
 // r = a^2 mod p.  44 IMAD.WIDE.U32 (28 cross products, doubled by a 1-bit shift, + 8 squares + 8 fold).
@@ -289,14 +380,24 @@ EDG_FE_MUL void fe_sq(fe &r, const fe &a) {
     for (int i = 0; i < 17; i++) w[i] = od[i] = 0;
     // cross products a_j a_i, j > i:  j = i+1, i+3, .. -> odd word i+j  -> od[2i + 0, 2, ..]
     //                                 j = i+2, i+4, .. -> even word i+j -> w[2i + 2, ..]
-#define EDG_SQ_ROW(i) cmad<(8 - (i)) / 2>(od + 2 * (i), a.v + (i) + 1, a.v[i]); cmad<(7 - (i)) / 2>(w + 2 * (i) + 2, a.v + (i) + 2, a.v[i]);
-    EDG_SQ_ROW(0) EDG_SQ_ROW(1) EDG_SQ_ROW(2) EDG_SQ_ROW(3) EDG_SQ_ROW(4) EDG_SQ_ROW(5) EDG_SQ_ROW(6)
-#undef EDG_SQ_ROW
+    // a row needs its carry-out word only when its top slot already holds a product (odd rows of od, rows 2 and 4 of w)
+#define EDG_SQ_OD(i, M) M<(8 - (i)) / 2>(od + 2 * (i), a.v + (i) + 1, a.v[i]);
+#define EDG_SQ_EV(i, M) M<(7 - (i)) / 2>(w + 2 * (i) + 2, a.v + (i) + 2, a.v[i]);
+    EDG_SQ_OD(0, cmadf) EDG_SQ_EV(0, cmadf)
+    EDG_SQ_OD(1, cmad)  EDG_SQ_EV(1, cmadf)
+    EDG_SQ_OD(2, cmadf) EDG_SQ_EV(2, cmad)
+    EDG_SQ_OD(3, cmad)  EDG_SQ_EV(3, cmadf)
+    EDG_SQ_OD(4, cmadf) EDG_SQ_EV(4, cmad)
+    EDG_SQ_OD(5, cmad)  EDG_SQ_EV(5, cmadf)
+    EDG_SQ_OD(6, cmadf)
+#undef EDG_SQ_OD
+#undef EDG_SQ_EV
     merge_odd(w, od);
 #pragma unroll
     for (int k = 15; k > 0; k--) w[k] = (w[k] << 1) | (w[k - 1] >> 31);        // x2 (word 0 holds no cross product)
     w[0] = 0;
     add_squares(w, a.v);
+    fe_fold_sq(r, w);
 #else
     for (int i = 0; i < 17; i++) w[i] = 0;
     for (int i = 0; i < 8; i++) {
@@ -304,8 +405,8 @@ EDG_FE_MUL void fe_sq(fe &r, const fe &a) {
         for (int j = 0; j < 8; j++) { const u64 t = mulw(a.v[j], a.v[i]) + w[i + j] + c; w[i + j] = (u32)t; c = t >> 32; }
         w[i + 8] = (u32)c;
     }
-#endif
     fe_fold512(r, w);
+#endif
 }
 
 // r = a * 121665 mod p.                     [reference: fld_scale, fld.c:184/:430; only s = 121665 is used, x25519.c:77]
