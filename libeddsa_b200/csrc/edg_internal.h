@@ -19,8 +19,12 @@ int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, int sm
 int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, int sm_count, void *stream);
 int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
                     const unsigned long long *off, unsigned long long fixed_len, int sm_count, void *stream);
+/* window table of the base point used by verify: built once per device, read-only afterwards */
+size_t edg_verify_table_bytes(void);
+int edg_verify_table_init(void *table, void *stream);
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
-                      const unsigned long long *off, unsigned long long fixed_len, void *scratch, int sm_count, void *stream);
+                      const unsigned long long *off, unsigned long long fixed_len, void *scratch, const void *table,
+                      int sm_count, void *stream);
 int edg_launch_pk_convert(size_t n, uint8_t *out, const uint8_t *in, int sm_count, void *stream);
 int edg_launch_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op, int sm_count, void *stream);
 int edg_launch_sk_convert(size_t n, uint8_t *out, const uint8_t *in, int sm_count, void *stream);

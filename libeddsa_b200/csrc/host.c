@@ -57,6 +57,7 @@ typedef struct {
     size_t in_cap, out_cap;
     void *scratch[EDG_NSLOT];
     size_t scratch_bytes;
+    void *wtab; /* verify: window table of the base point, built at context creation */
     pthread_mutex_t us_lock;
     struct { void *stream; void *buf; int used; } user_scratch[EDG_MAX_USER_STREAMS];
 } edg_dev_t;
@@ -147,6 +148,10 @@ static int dev_basic(int dev, edg_dev_t **out_ctx)
                 CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
                 CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
             }
+            CU(cudaMalloc(&c->wtab, edg_verify_table_bytes()));
+            rc = edg_verify_table_init(c->wtab, c->stream[0]);
+            if (rc) { rc = fail(rc, "window table build failed: %s", cudaGetErrorString((cudaError_t)rc)); goto out; }
+            CU(cudaStreamSynchronize(c->stream[0]));
             __sync_synchronize();
             c->ready = 1;
         out:
@@ -212,7 +217,7 @@ static int launch(edg_dev_t *c, edg_op_t op, size_t n, uint8_t *d_out, uint8_t *
     switch (op) {
     case OP_GENPUB: rc = edg_launch_genpub(n, d_out, d_in[0], c->sm_count, stream); break;
     case OP_SIGN: rc = edg_launch_sign(n, d_out, d_in[0], d_in[1], d_msgs, d_off, fixed_len, c->sm_count, stream); break;
-    case OP_VERIFY: rc = edg_launch_verify(n, d_out, d_in[0], d_in[1], d_msgs, d_off, fixed_len, scratch, c->sm_count, stream); break;
+    case OP_VERIFY: rc = edg_launch_verify(n, d_out, d_in[0], d_in[1], d_msgs, d_off, fixed_len, scratch, c->wtab, c->sm_count, stream); break;
     case OP_X25519: rc = edg_launch_x25519(n, d_out, d_in[0], d_in[1], c->sm_count, stream); break;
     case OP_X25519_BASE: rc = edg_launch_x25519_base(n, d_out, d_in[0], c->sm_count, stream); break;
     case OP_PK_CONV: rc = edg_launch_pk_convert(n, d_out, d_in[0], c->sm_count, stream); break;
@@ -581,6 +586,8 @@ void eddsa_b200_shutdown(void)
         }
         for (i = 0; i < EDG_MAX_USER_STREAMS; i++)
             if (c->user_scratch[i].used) { cudaFree(c->user_scratch[i].buf); c->user_scratch[i].used = 0; }
+        if (c->wtab) cudaFree(c->wtab);
+        c->wtab = NULL;
         c->in_cap = c->out_cap = 0;
         c->ready = 0;
         pthread_mutex_unlock(&c->lock);

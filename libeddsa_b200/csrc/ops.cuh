@@ -243,8 +243,110 @@ EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
 // flow across the warp; the reference's vartime JSF chain ed.c:455-507 computes the same group
 // element for every on-curve A because the addition law is complete).
 //   qtab : this thread's scratch for 0..8 times (-A) in cached form, 9 x 32 words
-//   small: BASE_SMALL (0..8 times B, affine precomputed), 9 x EDG_SMALL_STRIDE words, in shared memory
+//   wtab : window table of the base point, e * B for e = 0 .. 2^(EDG_BWIN-1) in affine precomputed form
+//          (24 words each), built once per device by wtab_build8 and resident in L2: B is fixed, so its
+//          scalar is cut into signed EDG_BWIN-bit digits — 16 additions per signature instead of the 64
+//          a 4-bit window needs (the reference's JSF chain spends ~85 on B, ed.c:479-506).
 // ------------------------------------------------------------------------------------------------
+#ifndef EDG_BWIN
+#define EDG_BWIN 16
+#endif
+#define EDG_WTAB_ENTRIES ((1u << (EDG_BWIN - 1)) + 1u)
+#define EDG_WTAB_WORDS (EDG_WTAB_ENTRIES * 24u)
+
+// Signed EDG_BWIN-bit digits of x in [0, L), in place: x += 2^(W-1) * sum 2^(W k) (no overflow: x < 2^253);
+// digit_k = ((x >> W k) mod 2^W) - 2^(W-1) in [-2^(W-1), 2^(W-1)) and sum digit_k 2^(W k) = the original x.
+EDG_HD void sc_recode_window(u32 x[8]) {
+    u32 off = 0;
+#pragma unroll
+    for (int k = 0; k < 32 / EDG_BWIN; k++) off |= 1u << (EDG_BWIN * k + EDG_BWIN - 1);
+    u32 carry = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u64 t = (u64)x[i] + off + carry;
+        x[i] = (u32)t;
+        carry = (u32)(t >> 32);
+    }
+}
+
+// (x, y) = (X, Y) * zinv -> affine precomputed form with canonical words
+EDG_HD void ge_pre_from_p3(ge_pre &o, const ge_p3 &p, const fe &zinv) {
+    const fe d2 = EDG_FE_2D;
+    fe x, y, t;
+    fe_mul(x, p.X, zinv);
+    fe_mul(y, p.Y, zinv);
+    fe_add(t, y, x); fe_canon(o.ypx, t);
+    fe_sub(t, y, x); fe_canon(o.ymx, t);
+    fe_mul(t, x, y);
+    fe_mul(t, t, d2); fe_canon(o.xy2d, t);
+}
+
+EDG_HD void ge_pre_store(u32 *dst, const ge_pre &q) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { dst[i] = q.ypx.v[i]; dst[8 + i] = q.ymx.v[i]; dst[16 + i] = q.xy2d.v[i]; }
+}
+
+// out (24 words) = affine precomputed form of 2^doublings * B, B decoded from its standard encoding (y = 4/5, x even)
+EDG_HD void wtab_base(u32 *out, int doublings) {
+    const u32 enc[8] = {0x66666658u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u, 0x66666666u};
+    ge_p3 P;
+    ge_frombytes(P, enc, false);
+#pragma unroll 1
+    for (int i = 0; i < doublings; i++) ge_dbl(P, P, true);
+    fe zi;
+    fe_inv(zi, P.Z);
+    ge_pre q;
+    ge_pre_from_p3(q, P, zi);
+    ge_pre_store(out, q);
+}
+
+// out[k] (24 words each) = (e0 + k) * P for k = 0..7, P given in affine precomputed form; one shared inversion
+EDG_HD void wtab_build8(u32 *out, const u32 *base, u32 e0) {
+    ge_pre P;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { P.ypx.v[i] = base[i]; P.ymx.v[i] = base[8 + i]; P.xy2d.v[i] = base[16 + i]; }
+    ge_p3 Q;
+    ge_identity(Q);
+#pragma unroll 1
+    for (int bit = 31; bit >= 0; bit--) {                 // e0 * P, plain double-and-add (public data)
+        ge_dbl(Q, Q, true);
+        if ((e0 >> bit) & 1u) ge_madd(Q, Q, P, true);
+    }
+    fe X[8], Y[8], Z[8];
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        fe_copy(X[k], Q.X); fe_copy(Y[k], Q.Y); fe_copy(Z[k], Q.Z);
+        ge_madd(Q, Q, P, true);
+    }
+    fe_batch_inv(Z, 8);
+#pragma unroll 1
+    for (int k = 0; k < 8; k++) {
+        ge_p3 T;
+        fe_copy(T.X, X[k]); fe_copy(T.Y, Y[k]);
+        ge_pre q;
+        ge_pre_from_p3(q, T, Z[k]);
+        ge_pre_store(out + 24 * k, q);
+    }
+}
+
+// entry |digit| of a window table in global memory, negated when digit < 0 (public data: direct index)
+EDG_HD void ge_pre_load_wtab(ge_pre &t, const u32 *tbl, int digit) {
+    const u32 neg = (u32)(digit >> 31);
+    const u32 absd = ((u32)digit ^ neg) - neg;
+    const u32 *e = tbl + 24u * absd;
+    u32 w[24];
+#if defined(__CUDA_ARCH__)
+    const uint4 *e4 = reinterpret_cast<const uint4 *>(e);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const uint4 v = __ldg(e4 + i); w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+#else
+    for (int i = 0; i < 24; i++) w[i] = e[i];
+#endif
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t.ypx.v[i] = w[i]; t.ymx.v[i] = w[8 + i]; t.xy2d.v[i] = w[16 + i]; }
+    ge_pre_cneg(t, neg);
+}
+
 EDG_HD void load_words8(u32 w[8], const u32 *src) {
 #if defined(__CUDA_ARCH__)
     const uint4 *p = reinterpret_cast<const uint4 *>(src);
@@ -258,7 +360,7 @@ EDG_HD void load_words8(u32 w[8], const u32 *src) {
 // sig / pub point at this signature's 64 / 32 bytes (16-byte aligned); they are re-read where
 // needed instead of being kept live in registers across the scalar-multiplication loop.
 // front: C = S*B + t*(-A) in projective form; returns the on-curve mask of A
-EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
+EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *wtab) {
     u32 et[8], es[8];
     {
         // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
@@ -276,8 +378,8 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
         sc_reduce512(t, h);
         sc_recode_radix16(et, t);
         load_words8(h, sig + 8);
-        sc_reduce256(t, h);                               // no range check on S (Q1)               :163
-        sc_recode_radix16(es, t);
+        sc_reduce256(es, h);                              // no range check on S (Q1)               :163
+        sc_recode_window(es);
     }
 
     // table k*Q for Q = -A, k = 0..8, cached form, in this thread's scratch                       :151, :174-175
@@ -300,21 +402,29 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
         }
     }
 
-    // Straus main loop.  Each window is six steps through ONE loop body — four doublings, the addition of
-    // the (-A)-table entry, the addition of the B-table entry — because doubling and addition end in the
-    // same four products (X3 = E F, Y3 = G H, Z3 = F G, T3 = E H): sharing that tail halves the loop's
-    // instruction footprint (the fully inlined form overflowed the instruction cache: 1.1 stall cycles per
-    // issue with reason no_instruction, profiles/r01_summary.md).  T3 is only computed when an addition follows.
+    // Straus main loop.  Each 4-bit window of t is up to six steps through ONE loop body — four doublings, the
+    // addition of the (-A)-table entry and, where an EDG_BWIN-bit window of S starts, the addition of the B-table
+    // entry — because doubling and addition end in the same four products (X3 = E F, Y3 = G H, Z3 = F G,
+    // T3 = E H): sharing that tail halves the loop's instruction footprint (the fully inlined form overflowed the
+    // instruction cache, profiles/r01_summary.md).  T3 is only computed when an addition follows.
     ge_identity(R);
 #pragma unroll 1
     for (int j = 63; j >= 0; j--) {
         const int dt = (int)(et[7] >> 28) - 8;
-        const int ds = (int)(es[7] >> 28) - 8;
 #pragma unroll
-        for (int i = 7; i > 0; i--) { et[i] = (et[i] << 4) | (et[i - 1] >> 28); es[i] = (es[i] << 4) | (es[i - 1] >> 28); }
-        et[0] <<= 4; es[0] <<= 4;
+        for (int i = 7; i > 0; i--) et[i] = (et[i] << 4) | (et[i - 1] >> 28);
+        et[0] <<= 4;
+        const bool has_b = ((4 * j) % EDG_BWIN) == 0;
+        int ds = 0;
+        if (has_b) {
+            ds = (int)(es[7] >> (32 - EDG_BWIN)) - (1 << (EDG_BWIN - 1));
+#pragma unroll
+            for (int i = 7; i > 0; i--) es[i] = (es[i] << EDG_BWIN) | (es[i - 1] >> (32 - EDG_BWIN));
+            es[0] <<= EDG_BWIN;
+        }
+        const int last = has_b ? 6 : 5;
 #pragma unroll 1
-        for (int step = (j == 63 ? 4 : 0); step < 6; step++) {
+        for (int step = (j == 63 ? 4 : 0); step < last; step++) {
             fe e, f, g, h;
             if (step < 4) {                                   // doubling prologue                 [ed_double, ed.c:211]
                 fe a, b, c, s;
@@ -338,9 +448,9 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
                     ge_cached_cneg(q, neg);
                     fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.t2d);
                     fe_mul(d, R.Z, q.z2);
-                } else {                                      // ds * B: affine entry from shared memory (Z2 = 1)
+                } else {                                      // ds * B: affine entry of the window table (Z2 = 1)
                     ge_pre q;
-                    ge_pre_load(q, small, ds);
+                    ge_pre_load_wtab(q, wtab, ds);
                     fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.xy2d);
                     fe_dbl(d, R.Z);
                 }
@@ -357,7 +467,7 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
             fe_mul(R.X, e, f);                                // shared tail
             fe_mul(R.Y, g, h);
             fe_mul(R.Z, f, g);
-            if (step == 3 || step == 4) fe_mul(R.T, e, h);
+            if (step == 3 || (step == 4 && has_b)) fe_mul(R.T, e, h);
         }
     }
     return on_curve;
@@ -374,9 +484,9 @@ EDG_HD u32 ed25519_verify_back(const fe &X, const fe &Y, const fe &zinv, u32 on_
     return (diff == 0 ? 1u : 0u) & (on_curve & 1u);
 }
 
-EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *small) {
+EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *wtab) {
     ge_p3 R;
-    const u32 on_curve = ed25519_verify_front(R, sig, pub, msg, len, qtab, small);
+    const u32 on_curve = ed25519_verify_front(R, sig, pub, msg, len, qtab, wtab);
     fe_inv(R.Z, R.Z);
     return ed25519_verify_back(R.X, R.Y, R.Z, on_curve, sig);
 }
