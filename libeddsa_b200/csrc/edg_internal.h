@@ -4,7 +4,6 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define EDG_QTAB_WORDS 288 /* verify: 9 cached points x 32 words of per-thread scratch */
 
 #ifdef __cplusplus
 extern "C" {
@@ -22,6 +21,7 @@ int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *p
 /* window table of the base point used by verify: built once per device, read-only afterwards */
 size_t edg_verify_table_bytes(void);
 int edg_verify_table_init(void *table, void *stream);
+unsigned edg_verify_launches(size_t n, int sm_count); /* kernels one edg_launch_verify(n) launches */
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
                       const unsigned long long *off, unsigned long long fixed_len, void *scratch, const void *table,
                       int sm_count, void *stream);

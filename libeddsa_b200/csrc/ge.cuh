@@ -195,7 +195,7 @@ EDG_HD void ge_pre_load(ge_pre &t, const u32 *tbl, int digit) {
 // off-curve y the reference goes on with x = sqrt(-1)*beta (garbage) — callers apply the SURVEY Q5
 // policy.  If negate is set the result is -P (x and t negated), which is what verify needs.
 //                                                                                 [ed_import, ed.c:100-149]
-EDG_HD u32 ge_frombytes(ge_p3 &p, const u32 in[8], bool negate) {
+EDG_HD u32 ge_frombytes(ge_p3 &p, const u32 in[8], bool negate, u32 *canonical = 0) {
     const fe d = EDG_FE_D, sqrtm1 = EDG_FE_SQRTM1;
     u32 w[8];
 #pragma unroll
@@ -226,6 +226,16 @@ EDG_HD u32 ge_frombytes(ge_p3 &p, const u32 in[8], bool negate) {
     fe_mul(t, beta, sqrtm1);
     fe_select(x, t, beta, is_root);                      // x = is_root ? beta : j beta        ed.c:140-142
     fe_canon(x, x);
+    if (canonical) {
+        // the 32 bytes are what ed_export (ed.c:155-169) would emit for this point: y < p, and sign 0 when x = 0
+        u32 s[8], xnz = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { s[i] = w[i]; xnz |= x.v[i]; }
+        addw8(s, 19u);                                   // y + 19 reaches bit 255  <=>  y >= p
+        const u32 y_ok = (s[7] >> 31) ^ 1u;
+        const u32 x_ok = (xnz != 0 || sign == 0) ? 1u : 0u;
+        *canonical = 0u - (y_ok & x_ok);
+    }
     u32 flip = 0u - ((sign ^ (x.v[0] & 1u)) & 1u);       // ed.c:143-144
     if (negate) flip = ~flip;
     fe_neg(t, x);                                        // -0 stays == 0 mod p

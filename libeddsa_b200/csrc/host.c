@@ -226,7 +226,7 @@ static int launch(edg_dev_t *c, edg_op_t op, size_t n, uint8_t *d_out, uint8_t *
     default: return fail(EDDSA_B200_EINVAL, "unknown operation");
     }
     if (rc) return fail(rc, "kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    if (n) __sync_fetch_and_add(&g_launches, 1ULL);
+    if (n) __sync_fetch_and_add(&g_launches, op == OP_VERIFY ? (unsigned long long)edg_verify_launches(n, c->sm_count) : 1ULL);
     return 0;
 }
 

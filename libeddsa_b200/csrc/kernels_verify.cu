@@ -1,52 +1,50 @@
-// Verification kernel (sm_100a): one signature per thread — SHA-512 challenge, decompression of A,
-// Straus double-scalar multiplication S*B + t*(-A) with fixed signed 4-bit windows (uniform control
-// flow), encoding and byte comparison.  Public data only, so table lookups are direct-indexed.
+// Verification kernels (sm_100a), one signature per thread, in two stages (ops.cuh: ed25519_verify_front / _loop):
+//   k_verify_front  SHA-512 challenge, half-gcd (hgcd.cuh), decompression of A and R, the two 8-entry tables
+//   k_verify        Straus multi-scalar multiplication over ~33 signed 4-bit windows (uniform control flow) and the
+//                   projective comparison with the neutral element
+// Public data only, so table lookups are direct-indexed.
 // Also hosts pk_ed25519_to_x25519 (it shares the decompression).
 // Replaces ed25519_verify / pk_ed25519_to_x25519: /root/reference/lib/ed25519-sha512.c:148-237.
 #include "kernel_common.cuh"
 using namespace edg;
 
+#ifndef EDG_VERIFY_WAVES
+#define EDG_VERIFY_WAVES 4  /* waves of resident threads per pass: sizes the per-signature records in scratch */
+#endif
 #ifndef EDG_LB_VERIFY
 #define EDG_LB_VERIFY 4     /* min resident blocks per SM the register allocator must allow: 128 registers, 4 warps/SMSP
                                (measured +4 % over 3 blocks, profiles/r01_summary.md) */
 #endif
 namespace {
 
-__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
-                                                     const unsigned long long *off, unsigned long long fixed_len, u32 *scratch,
-                                                     const u32 *__restrict__ wtab) {
-    u32 *qtab = scratch + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * EDG_QTAB_WORDS;
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
-        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH];
-        u32 on_curve = 0;                                      // bit k: public key of the k-th signature decoded to a curve point
-        int cnt = 0;
-#pragma unroll 1
-        for (int k = 0; k < EDG_BATCH; k++) {                 // phase 1: C = S*B + t*(-A), projective
-            const size_t i = i0 + (size_t)k * T;
-            if (i >= n) break;
-            const uint8_t *m; u64 len;
-            msg_of(m, len, msgs, off, fixed_len, i);
-            ge_p3 R;
-            const u32 oc = ed25519_verify_front(R, reinterpret_cast<const u32 *>(sig + 64 * i), reinterpret_cast<const u32 *>(pub + 32 * i),
-                                                m, len, qtab, wtab);
-            on_curve |= (oc & 1u) << k;
-            fe_copy(X[k], R.X); fe_copy(Y[k], R.Y); fe_copy(Z[k], R.Z);
-            cnt++;
-        }
-        fe_batch_inv(Z, cnt);                                  // phase 2: one inversion per batch
-#pragma unroll 1
-        for (int k = 0; k < cnt; k++) {                        // phase 3: encode and compare with the signature's R bytes
-            const size_t i = i0 + (size_t)k * T;
-            ok[i] = (uint8_t)ed25519_verify_back(X[k], Y[k], Z[k], (on_curve >> k) & 1u, reinterpret_cast<const u32 *>(sig + 64 * i));
-        }
-    }
+// stage 1: one signature per thread -> its EDG_VSTATE_WORDS-word record
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t n, size_t first, const uint8_t *sig, const uint8_t *pub,
+                                                     const uint8_t *msgs, const unsigned long long *off, unsigned long long fixed_len,
+                                                     u32 *state) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const size_t i = first + k;
+    const uint8_t *m; u64 len;
+    msg_of(m, len, msgs, off, fixed_len, i);
+    ed25519_verify_front(state + k * EDG_VSTATE_WORDS, reinterpret_cast<const u32 *>(sig + 64 * i), reinterpret_cast<const u32 *>(pub + 32 * i), m, len);
 }
 
-// Window table of the base point (built once per device): entry e = e * B, e = 0 .. 2^(EDG_BWIN-1).
-__global__ void k_wtab_base(u32 *base, int doublings) { wtab_base(base, doublings); }
+// stage 2: the window loop.  Whole warps stay together (the trip count is agreed per warp with a full-mask
+// reduction): lanes past the end redo the last record and drop the result.
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify(size_t n, uint8_t *ok, const u32 *state, const u32 *__restrict__ wtab) {
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((k & ~(size_t)31) >= n) return;
+    const size_t kk = k < n ? k : n - 1;
+    const u32 r = ed25519_verify_loop(state + kk * EDG_VSTATE_WORDS, wtab);
+    if (k < n) ok[k] = (uint8_t)r;
+}
 
-__global__ void __launch_bounds__(kThreads) k_wtab_build(u32 *table, const u32 *base) {
+// Window tables of B and 2^128 B (built once per device): entry e = e * P, e = 0 .. 2^15.
+__global__ void k_wtab_base(u32 *base) { wtab_base(base + 24 * threadIdx.x, 128 * (int)threadIdx.x); }
+
+__global__ void __launch_bounds__(kThreads) k_wtab_build(u32 *tables, const u32 *bases) {
+    u32 *table = tables + (size_t)blockIdx.y * EDG_WTAB_WORDS;
+    const u32 *base = bases + 24 * blockIdx.y;
     const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g == 0) {
         for (int i = 0; i < 24; i++) table[i] = (i == 0 || i == 8) ? 1u : 0u;      // neutral element (1, 1, 0)
@@ -67,29 +65,43 @@ __global__ void __launch_bounds__(kThreads) k_pk_convert(size_t n, uint8_t *out,
 
 extern "C" {
 
-size_t edg_verify_scratch_bytes(int sm_count) {
+// signatures per pass: a whole number of waves of the loop kernel (resident threads of the device)
+static size_t verify_chunk(int sm_count) {
     int bps = 0;
     grid_for(k_verify, (size_t)1 << 40, 0, sm_count, &bps);
-    return (size_t)sm_count * bps * kThreads * EDG_QTAB_WORDS * sizeof(u32);
+    return (size_t)sm_count * bps * kThreads * EDG_VERIFY_WAVES;
 }
 
-size_t edg_verify_table_bytes(void) { return ((size_t)EDG_WTAB_WORDS + 24) * sizeof(u32); }
+size_t edg_verify_scratch_bytes(int sm_count) { return verify_chunk(sm_count) * EDG_VSTATE_WORDS * sizeof(u32); }
 
-// table: edg_verify_table_bytes() of device memory; the last 24 words are scratch for the affine base point
+size_t edg_verify_table_bytes(void) { return (2 * (size_t)EDG_WTAB_WORDS + 48) * sizeof(u32); }
+
+// table: edg_verify_table_bytes() of device memory = the tables of B and 2^128 B; the last 48 words are the two
+// base points in affine form
 int edg_verify_table_init(void *table, void *stream) {
-    u32 *t = (u32 *)table, *base = t + EDG_WTAB_WORDS;
-    k_wtab_base<<<1, 1, 0, (cudaStream_t)stream>>>(base, 0);
+    u32 *t = (u32 *)table, *bases = t + 2 * (size_t)EDG_WTAB_WORDS;
+    k_wtab_base<<<1, 2, 0, (cudaStream_t)stream>>>(bases);
     const unsigned groups = (EDG_WTAB_ENTRIES - 1) / 8;
-    k_wtab_build<<<(groups + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(t, base);
+    k_wtab_build<<<dim3((groups + kThreads - 1) / kThreads, 2), kThreads, 0, (cudaStream_t)stream>>>(t, bases);
     return (int)cudaGetLastError();
+}
+
+// kernels edg_launch_verify(n, ..) launches: two per pass
+unsigned edg_verify_launches(size_t n, int sm_count) {
+    const size_t chunk = verify_chunk(sm_count);
+    return (unsigned)(2 * ((n + chunk - 1) / chunk));
 }
 
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
                       const unsigned long long *off, unsigned long long fixed_len, void *scratch, const void *table,
                       int sm_count, void *stream) {
-    if (n == 0) return 0;
-    int g = grid_for(k_verify, n, 0, sm_count, nullptr);
-    k_verify<<<g, kThreads, 0, (cudaStream_t)stream>>>(n, ok, sig, pub, msgs, off, fixed_len, (u32 *)scratch, (const u32 *)table);
+    const size_t chunk = verify_chunk(sm_count);
+    for (size_t first = 0; first < n; first += chunk) {
+        const size_t m = n - first < chunk ? n - first : chunk;
+        const unsigned blocks = (unsigned)((m + kThreads - 1) / kThreads);
+        k_verify_front<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch);
+        k_verify<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(m, ok + first, (const u32 *)scratch, (const u32 *)table);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -12,6 +12,7 @@
 #include "sc.cuh"
 #include "sha512.cuh"
 #include "ge.cuh"
+#include "hgcd.cuh"
 
 namespace edg {
 
@@ -357,15 +358,50 @@ EDG_HD void load_words8(u32 w[8], const u32 *src) {
 #endif
 }
 
-// sig / pub point at this signature's 64 / 32 bytes (16-byte aligned); they are re-read where
-// needed instead of being kept live in registers across the scalar-multiplication loop.
-// front: C = S*B + t*(-A) in projective form; returns the on-curve mask of A
-EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *wtab) {
-    u32 et[8], es[8];
+#if defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
+static int edg_last_nwin = 0;                              // host-only instrumentation (tests/host_sim): windows of the last verify
+#endif
+
+// Table k*Q, k = 0..8, in cached form, 9 x 32 words of this thread's scratch.       [ed_precompute, ed.c:436]
+EDG_HD void ge_cached_table(u32 *tab, ge_p3 &Q) {
+    ge_cached c, c1;
+    fe_set_u32(c.ypx, 1); fe_set_u32(c.ymx, 1); fe_set_u32(c.z2, 2); fe_set_u32(c.t2d, 0);
+    ge_cached_store(tab, c);
+    ge_to_cached(c1, Q);
+    ge_cached_store(tab + 32, c1);
+#pragma unroll 1
+    for (int k = 2; k <= 8; k++) {
+        ge_add_cached(Q, Q, c1, true);                    // k*Q = (k-1)*Q + Q
+        ge_to_cached(c, Q);
+        ge_cached_store(tab + 32 * k, c);
+    }
+}
+
+// signed nibble j of a recoded scalar held in (local) memory
+EDG_HD int sc_digit16(const u32 *e, int j) { return (int)((e[j >> 3] >> (4 * (j & 7))) & 15u) - 8; }
+
+// sig / pub point at this signature's 64 / 32 bytes (16-byte aligned).
+// Accept iff  encode(S*B - t*A) == sig[0..31]  and A decodes to a curve point (Q2, Q5 policy), decided as
+//   sig[0..31] canonical encoding of a curve point R'   and   (rho S)*B + tau*(-+A) + |rho|*(-R') == O
+// with the half-size (rho, tau) of hgcd.cuh.  Straus over 4-bit signed windows of tau and |rho| (tables of the
+// two variable points) and 16-bit signed windows of rho S (tables of B and 2^128 B, wtab: 2 x EDG_WTAB_WORDS
+// words, L2-resident), uniform control flow across the warp.
+//
+// Two stages with an EDG_VSTATE_WORDS-word record per signature in between, so that each can be its own kernel
+// (one kernel holding both overflowed the instruction cache: warps in the front part kept evicting the loop):
+//   front: challenge hash, half-gcd, |rho| S mod L, both decompressions, both tables
+//   loop : the window loop and the projective comparison with the neutral element
+// record: [0, 288) table of Q = -sign(rho) A, [288, 576) table of P = -R' (9 cached points x 32 words each),
+//         [576, 584) tau, [584, 592) |rho|, [592, 600) rho S recoded to signed 16-bit digits, [600] flags
+//         (bit 0: both points decoded and the R bytes are canonical), [601] windows needed.
+#define EDG_VSTATE_WORDS 608
+
+EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
+    u32 et[8], er[8], es[8], rho_neg;
     {
         // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
         u64 pre[8], st[8];
-        u32 h[16], t[8];
+        u32 h[16], t[8], s[8];
         load_words8(t, sig);
         load_words8(h, pub);
 #pragma unroll
@@ -376,55 +412,66 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
         sha512_prefixed<8>(st, pre, msg, len);
         sha512_state_to_le_words(h, st);
         sc_reduce512(t, h);
-        sc_recode_radix16(et, t);
+        half_gcd(er, rho_neg, et, t);                     // er = |rho|, et = tau
         load_words8(h, sig + 8);
-        sc_reduce256(es, h);                              // no range check on S (Q1)               :163
+        sc_reduce256(s, h);                               // no range check on S (Q1)               :163
+#pragma unroll
+        for (int i = 0; i < 8; i++) h[i] = 0;
+        sc_muladd(es, er, s, h);                          // |rho| S mod L
         sc_recode_window(es);
     }
+    const int bt = hg_bitlen8(et), br = hg_bitlen8(er);
+    int nwin = ((bt > br ? bt : br) + 5) >> 2;
+    nwin = nwin < 32 ? 32 : nwin;                         // all 16-bit windows of rho S sit below bit 128
+#pragma unroll
+    for (int i = 0; i < 8; i++) { state[576 + i] = et[i]; state[584 + i] = er[i]; state[592 + i] = es[i]; }
 
-    // table k*Q for Q = -A, k = 0..8, cached form, in this thread's scratch                       :151, :174-175
-    u32 on_curve;
+    // tables of Q = -sign(rho) A and P = -R'                                                      :151, :174-175
+    u32 good;
     {
         ge_p3 Q;
-        u32 a[8];
+        u32 a[8], canon;
         load_words8(a, pub);
-        on_curve = ge_frombytes(Q, a, true);
-        ge_cached c, c1;
-        fe_set_u32(c.ypx, 1); fe_set_u32(c.ymx, 1); fe_set_u32(c.z2, 2); fe_set_u32(c.t2d, 0);
-        ge_cached_store(qtab, c);
-        ge_to_cached(c1, Q);
-        ge_cached_store(qtab + 32, c1);
-#pragma unroll 1
-        for (int k = 2; k <= 8; k++) {
-            ge_add_cached(Q, Q, c1, true);                // k*Q = (k-1)*Q + Q
-            ge_to_cached(c, Q);
-            ge_cached_store(qtab + 32 * k, c);
-        }
+        good = ge_frombytes(Q, a, rho_neg == 0);
+        ge_cached_table(state, Q);
+        load_words8(a, sig);
+        good &= ge_frombytes(Q, a, true, &canon);
+        good &= canon;
+        ge_cached_table(state + 288, Q);
     }
+    state[600] = good & 1u;
+    state[601] = (u32)nwin;
+}
 
-    // Straus main loop.  Each 4-bit window of t is up to six steps through ONE loop body — four doublings, the
-    // addition of the (-A)-table entry and, where an EDG_BWIN-bit window of S starts, the addition of the B-table
-    // entry — because doubling and addition end in the same four products (X3 = E F, Y3 = G H, Z3 = F G,
-    // T3 = E H): sharing that tail halves the loop's instruction footprint (the fully inlined form overflowed the
-    // instruction cache, profiles/r01_summary.md).  T3 is only computed when an addition follows.
+EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab) {
+    u32 et[8], er[8], es[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { et[i] = state[576 + i]; er[i] = state[584 + i]; es[i] = state[592 + i]; }
+    const u32 good = state[600];
+    int nwin = (int)state[601];
+#if defined(__CUDA_ARCH__)
+    nwin = __reduce_max_sync(0xffffffffu, nwin);          // one trip count per warp (callers keep all 32 lanes here)
+#endif
+#if defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
+    edg_last_nwin = nwin;
+#endif
+    sc_recode_radix16_n(et, nwin);
+    sc_recode_radix16_n(er, nwin);
+    const u32 *qtab = state;
+
+    // Straus main loop.  Each 4-bit window is up to eight steps through ONE loop body — four doublings, the
+    // additions of the two scratch-table entries and, every fourth window below bit 128, of the two base-table
+    // entries — because doubling and addition end in the same four products (X3 = E F, Y3 = G H, Z3 = F G,
+    // T3 = E H): sharing that tail keeps the loop inside the instruction cache.  T3 is only computed when an
+    // addition follows.
+    ge_p3 R;
     ge_identity(R);
 #pragma unroll 1
-    for (int j = 63; j >= 0; j--) {
-        const int dt = (int)(et[7] >> 28) - 8;
-#pragma unroll
-        for (int i = 7; i > 0; i--) et[i] = (et[i] << 4) | (et[i - 1] >> 28);
-        et[0] <<= 4;
-        const bool has_b = ((4 * j) % EDG_BWIN) == 0;
-        int ds = 0;
-        if (has_b) {
-            ds = (int)(es[7] >> (32 - EDG_BWIN)) - (1 << (EDG_BWIN - 1));
-#pragma unroll
-            for (int i = 7; i > 0; i--) es[i] = (es[i] << EDG_BWIN) | (es[i - 1] >> (32 - EDG_BWIN));
-            es[0] <<= EDG_BWIN;
-        }
-        const int last = has_b ? 6 : 5;
+    for (int j = nwin - 1; j >= 0; j--) {
+        const bool has_b = ((j & 3) == 0) && j < 32;
+        const int last = has_b ? 8 : 6;
 #pragma unroll 1
-        for (int step = (j == 63 ? 4 : 0); step < last; step++) {
+        for (int step = (j == nwin - 1 ? 4 : 0); step < last; step++) {
             fe e, f, g, h;
             if (step < 4) {                                   // doubling prologue                 [ed_double, ed.c:211]
                 fe a, b, c, s;
@@ -440,17 +487,20 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
                 fe_add(f, c, g);
             } else {                                          // addition prologue                 [ed_add ed.c:175 / ed_add_pc :282]
                 fe ypx, ymx, t2d, a, b, c, d;
-                if (step == 4) {                              // dt * (-A): cached entry from this thread's scratch
-                    const u32 neg = (u32)(dt >> 31);
-                    const u32 absd = ((u32)dt ^ neg) - neg;
+                if (step < 6) {                               // digit * Q or digit * P: cached entry from this thread's scratch
+                    const int dg = sc_digit16(step == 4 ? et : er, j);
+                    const u32 neg = (u32)(dg >> 31);
+                    const u32 absd = ((u32)dg ^ neg) - neg;
                     ge_cached q;
-                    ge_cached_load(q, qtab + 32 * absd);
+                    ge_cached_load(q, qtab + (step == 4 ? 0 : 288) + 32 * absd);
                     ge_cached_cneg(q, neg);
                     fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.t2d);
                     fe_mul(d, R.Z, q.z2);
-                } else {                                      // ds * B: affine entry of the window table (Z2 = 1)
+                } else {                                      // digit * B or digit * 2^128 B: affine entry of a window table (Z2 = 1)
+                    const int k = (j >> 2) + (step == 6 ? 0 : 8);
+                    const int ds = (int)((es[k >> 1] >> (16 * (k & 1))) & 0xffffu) - 0x8000;
                     ge_pre q;
-                    ge_pre_load_wtab(q, wtab, ds);
+                    ge_pre_load_wtab(q, wtab + (step == 6 ? 0u : EDG_WTAB_WORDS), ds);
                     fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.xy2d);
                     fe_dbl(d, R.Z);
                 }
@@ -467,28 +517,17 @@ EDG_HD u32 ed25519_verify_front(ge_p3 &R, const u32 *sig, const u32 *pub, const 
             fe_mul(R.X, e, f);                                // shared tail
             fe_mul(R.Y, g, h);
             fe_mul(R.Z, f, g);
-            if (step == 3 || (step == 4 && has_b)) fe_mul(R.T, e, h);
+            if (step == 3 || step == 4 || step == 6 || (step == 5 && has_b)) fe_mul(R.T, e, h);
         }
     }
-    return on_curve;
+    // the sum is the neutral element (0 : 1 : 1)  <=>  X = 0 and Y = Z   (Z != 0: the addition law is complete)
+    const u32 is_o = fe_is_zero(R.X) & fe_eq(R.Y, R.Z);
+    return is_o & (good & 1u);
 }
 
-// back: accept iff encode(C) equals the first 32 signature bytes (Q2) and A was on the curve (Q5 policy)   :177-180
-EDG_HD u32 ed25519_verify_back(const fe &X, const fe &Y, const fe &zinv, u32 on_curve, const u32 *sig) {
-    u32 check[8], r8[8];
-    ge_tobytes_zinv(check, X, Y, zinv);
-    load_words8(r8, sig);
-    u32 diff = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) diff |= check[i] ^ r8[i];
-    return (diff == 0 ? 1u : 0u) & (on_curve & 1u);
-}
-
-EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *qtab, const u32 *wtab) {
-    ge_p3 R;
-    const u32 on_curve = ed25519_verify_front(R, sig, pub, msg, len, qtab, wtab);
-    fe_inv(R.Z, R.Z);
-    return ed25519_verify_back(R.X, R.Y, R.Z, on_curve, sig);
+EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *state, const u32 *wtab) {
+    ed25519_verify_front(state, sig, pub, msg, len);
+    return ed25519_verify_loop(state, wtab);
 }
 
 // pk_ed25519_to_x25519: u = (1 + y) / (1 - y) of the decoded point.   [ed25519-sha512.c:187-237]

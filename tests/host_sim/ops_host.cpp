@@ -22,18 +22,20 @@ static const u32 *host_wtab() {
     static u32 *tab = 0;
     if (!tab) {
         const unsigned long m = edg_cnt_mul, q = edg_cnt_sq;
-        tab = new u32[EDG_WTAB_WORDS];
-        u32 base[24];
-        wtab_base(base, 0);
-        for (int i = 0; i < 24; i++) tab[i] = (i == 0 || i == 8) ? 1u : 0u;
-        for (u32 g = 0; 8u * g + 8u < EDG_WTAB_ENTRIES; g++) wtab_build8(tab + 24u * (8u * g + 1u), base, 8u * g + 1u);
+        tab = new u32[2 * (size_t)EDG_WTAB_WORDS];
+        for (int m = 0; m < 2; m++) {
+            u32 base[24], *tb = tab + m * (size_t)EDG_WTAB_WORDS;
+            wtab_base(base, 128 * m);
+            for (int i = 0; i < 24; i++) tb[i] = (i == 0 || i == 8) ? 1u : 0u;
+            for (u32 g = 0; 8u * g + 8u < EDG_WTAB_ENTRIES; g++) wtab_build8(tb + 24u * (8u * g + 1u), base, 8u * g + 1u);
+        }
         edg_cnt_mul = m; edg_cnt_sq = q;
     }
     return tab;
 }
 const uint32_t *hs_wtab(uint32_t *entries) { *entries = EDG_WTAB_ENTRIES; return host_wtab(); }
 int hs_verify(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64_t len) {
-    u32 s[16], p[8], qtab[288]; memcpy(s, sig, 64); memcpy(p, pub, 32);
+    u32 s[16], p[8], qtab[EDG_VSTATE_WORDS]; memcpy(s, sig, 64); memcpy(p, pub, 32);
     const u32 *wt = host_wtab();
     return (int)ed25519_verify_op(s, p, msg, len, qtab, wt);
 }
@@ -45,5 +47,7 @@ void hs_batch_inv(uint8_t *z, int cnt) {   // z: cnt x 32 bytes, in place
     fe_batch_inv(t, cnt);
     for (int k = 0; k < cnt; k++) { u32 w[8]; fe_to_words(w, t[k]); memcpy(z + 32 * k, w, 32); }
 }
+int hs_last_nwin(void) { return edg_last_nwin; }
+void hs_half_gcd(uint32_t *rho_abs, uint32_t *rho_neg, uint32_t *tau, const uint32_t *t) { u32 n; half_gcd(rho_abs, n, tau, t); *rho_neg = n; }
 void hs_counts(unsigned long *mul, unsigned long *sq, int reset) { *mul = edg_cnt_mul; *sq = edg_cnt_sq; if (reset) edg_cnt_mul = edg_cnt_sq = 0; }
 }

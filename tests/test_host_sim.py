@@ -188,6 +188,35 @@ def test_ops_adversarial_verify(ops):
     assert not bad, bad[:10]
 
 
+def test_half_gcd(ops):
+    """hgcd.cuh: (rho, tau) is a lattice vector (tau = rho t mod 8L), rho is odd, and both are short — for random t,
+    for structured t (tiny, huge partial quotients, even-rho traps) and for the documented fallback."""
+    L = 2**252 + 27742317777372353535851937790883648493
+    N = 8 * L
+    rng = random.Random(11)
+    ts = [0, 1, 2, 3, 5, 2**127, 2**128 - 1, 2**128, 2**128 + 1, L - 1, L - 2, (N + 1) // 2 % L, (L + 1) // 2, L // 3, L // 5,
+          2**200, 2**252, 2**251 + 7, (1 << 129) + 1, N // (2**64 + 13) % L, pow(3, -1, N) % L, pow(5, -1, N) % L,
+          pow(2**64 + 1, -1, N) % L, pow(2**126 + 1, -1, N) % L, pow(2**130 + 3, -1, N) % L]
+    ts += [rng.getrandbits(k) % L for k in (16, 64, 100, 128, 129, 160, 200, 252) for _ in range(40)]
+    ts += [rng.randrange(L) for _ in range(3000)]
+    rho = (ctypes.c_uint32 * 8)(); tau = (ctypes.c_uint32 * 8)(); neg = ctypes.c_uint32()
+    worst = 0; falls = 0
+    for t in ts:
+        tw = (ctypes.c_uint32 * 8)(*[(t >> (32 * i)) & 0xffffffff for i in range(8)])
+        ops.hs_half_gcd(rho, ctypes.byref(neg), tau, tw)
+        r = sum(int(rho[i]) << (32 * i) for i in range(8)); ta = sum(int(tau[i]) << (32 * i) for i in range(8))
+        r = -r if neg.value else r
+        assert r % 2 == 1, (t, r)
+        assert (r * t - ta) % N == 0, (t, r, ta)
+        if abs(r) == 1 and ta == t and t >= 2**128:
+            falls += 1                                   # fallback (rho, tau) = (1, t): allowed, must be rare
+        else:
+            assert ta < 2**128 and abs(r) < 2**160, (t, r, ta)
+            worst = max(worst, abs(r).bit_length(), ta.bit_length())
+    assert falls <= 10, falls                      # only structured t (short even vectors such as t = L - 1) may fall back
+    assert worst <= 150, worst
+
+
 def test_batch_inversion(ops):
     """Montgomery's trick shares one exponentiation among up to 8 values; zeros (any representative)
     stay zero and do not poison their neighbours (inv(0) = 0)."""
@@ -230,7 +259,7 @@ def test_field_op_counts(ops):
     ops.hs_sign(out, sec[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
     assert counts() == bench.OURS_FM_SINGLE["sign"]
     assert ops.hs_verify(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i]))) == 1
-    assert counts() == bench.OURS_FM_SINGLE["verify"]
+    assert counts() == bench.verify_fm(ops.hs_last_nwin()) and 32 <= ops.hs_last_nwin() <= 34
     ops.hs_x25519_base(out, sec[i].tobytes())
     assert counts() == bench.OURS_FM_SINGLE["x25519_base"]
     ops.hs_x25519(out, sec[i].tobytes(), pub[i].tobytes())

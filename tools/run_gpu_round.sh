@@ -7,7 +7,7 @@ python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_referen
 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" != "noprof" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 > gpurun_out/bench_under_ncu.log 2>&1
-for k in k_verify k_x25519 k_sign k_genpub; do
+for k in k_verify k_verify_front k_x25519 k_sign k_genpub; do
 ncu --set full --clock-control none --import-source on -k regex:${k}\$ -s 1 -c 1 -o gpurun_out/prof_${k} -f python tools/prof_driver.py > gpurun_out/prof_${k}.log 2>&1
 done
 fi
