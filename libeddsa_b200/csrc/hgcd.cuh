@@ -41,105 +41,149 @@ EDG_HD int hg_bitlen8(const u32 x[8]) {
     return n;
 }
 
-// (x[h], x[h-1]) as one 64-bit value, 3 <= h <= 7 (no dynamically indexed registers)
-EDG_HD u64 hg_top2(const u32 x[8], int h) {
-    u32 a, b;
-    if (h == 7) { a = x[7]; b = x[6]; }
-    else if (h == 6) { a = x[6]; b = x[5]; }
-    else if (h == 5) { a = x[5]; b = x[4]; }
-    else if (h == 4) { a = x[4]; b = x[3]; }
-    else { a = x[3]; b = x[2]; }
-    return ((u64)a << 32) | b;
+// bits [s, s + 32) of an 8-word value, 0 <= s <= 224 (no dynamically indexed registers: selection chain)
+EDG_HD u32 hg_extract32(const u32 x[8], int s) {
+    const int w = s >> 5, sh = s & 31;
+    u32 lo = 0, hi = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        lo = (w == i) ? x[i] : lo;
+        if (i + 1 < 8) hi = (w == i) ? x[i + 1] : hi;
+    }
+    return (u32)(((((u64)hi) << 32) | lo) >> sh);
 }
 
-// u -= q x  on the remainders,  mu += q xm  on the cofactor magnitudes (q x <= ru is the caller's business)
-EDG_HD void hg_step(u32 ru[8], u32 mu[5], const u32 x[8], const u32 xm[5], u32 q) {
-    u64 carry = 0;
+// out = a x - b y  modulo 2^(32 W): two's complement W-word values, small non-negative multipliers
+template <int W>
+EDG_HD void hg_lin(u32 *out, const u32 *x, u32 a, const u32 *y, u32 b) {
+    u64 ca = 0, cb = 0;
+    u32 borrow = 0;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const u64 pa = mulw(a, x[i]) + ca;
+        const u64 pb = mulw(b, y[i]) + cb;
+        ca = pa >> 32;
+        cb = pb >> 32;
+        const u64 d = (u64)(u32)pa - (u32)pb - borrow;
+        out[i] = (u32)d;
+        borrow = (u32)(d >> 63);
+    }
+}
+
+template <int W>
+EDG_HD void hg_neg(u32 *x) {
+    u32 carry = 1;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const u64 t = (u64)(~x[i]) + carry;
+        x[i] = (u32)t;
+        carry = (u32)(t >> 32);
+    }
+}
+
+// 1 if x < y (8-word unsigned)
+EDG_HD u32 hg_less8(const u32 x[8], const u32 y[8]) {
     u32 borrow = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const u64 p = mulw(q, x[i]) + carry;
-        carry = p >> 32;
-        const u64 d = (u64)ru[i] - (u32)p - borrow;
-        ru[i] = (u32)d;
+        const u64 d = (u64)x[i] - y[i] - borrow;
         borrow = (u32)(d >> 63);
     }
-    carry = 0;
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-        const u64 p = mulw(q, xm[i]) + mu[i] + carry;
-        mu[i] = (u32)p;
-        carry = p >> 32;
-    }
+    return borrow;
 }
 
 // (rho, tau): tau = rho * t (mod 8L), rho odd, rho = (rho_neg ? -1 : 1) * rho_abs.  t < L.
 // Normal case: rho_abs < 2^160 (typically < 2^129), tau < 2^128.  Fallback: rho = 1, tau = t.
+//
+// Lattice basis u = (bu, ru), v = (bv, rv): remainders ru >= rv >= 0 as 8-word unsigned values, cofactors bu, bv
+// as 6-word two's complement values; every step is unimodular, so u and v always generate
+// {(b, r) : r = b t mod 8L} — the result's validity never depends on the quotients being exact.
+//   * Lehmer step: run Euclid on the leading 32 bits (x, y) of (ru, rv) while the accumulated cofactors stay
+//     below 2^16 and the remainder stays above the 2^128 target, then apply the 2 x 2 matrix to the long numbers
+//     at once (signs fixed up afterwards if the approximation went one step too far);
+//   * single step with an under-estimated quotient when the leading words allow no Lehmer step (large partial
+//     quotient, or the last step across 2^128).
 EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8]) {
     const u32 N8L[8] = EDG_SC_8L_INIT;
-    // lattice vectors u = (-+mu, ru), v = (+-mv, rv) with ru >= rv >= 0 and mu rv + mv ru = 8L throughout
-    u32 ru[8], rv[8], mu[5], mv[5];
+    u32 ru[8], rv[8], bu[6], bv[6];
 #pragma unroll
     for (int i = 0; i < 8; i++) { ru[i] = N8L[i]; rv[i] = t[i]; }
 #pragma unroll
-    for (int i = 0; i < 5; i++) { mu[i] = 0; mv[i] = 0; }
-    mv[0] = 1;
-    u32 sv = 0;                                            // sign of v's first coordinate (1 = negative)
+    for (int i = 0; i < 6; i++) { bu[i] = 0; bv[i] = 0; }
+    bv[0] = 1;
     bool fallback = false;
 #pragma unroll 1
     for (;;) {
         const bool big = (rv[4] | rv[5] | rv[6] | rv[7]) != 0;      // rv >= 2^128: keep reducing
         if (!big) {
-            if (mv[0] & 1u) break;                                   // odd rho: done
+            if (bv[0] & 1u) break;                                   // odd rho: done
             if (rv[3] == 0) { fallback = true; break; }              // next vector could exceed 160 bits (rv < 2^96)
         }
-        // quotient estimate from the leading 32 bits of ru and the aligned bits of rv: 1 <= q <= floor(ru / rv).
-        // Here ru >= rv >= 2^96, so the leading word of ru is word 3 or higher.
-        const int h = ru[7] ? 7 : (ru[6] ? 6 : (ru[5] ? 5 : (ru[4] ? 4 : 3)));
-        const u64 u2 = hg_top2(ru, h);
-        const int c = hg_clz((u32)(u2 >> 32));
-        const u32 U = (u32)((u2 << c) >> 32);
-        const u32 V = (u32)((hg_top2(rv, h) << c) >> 32);
-        if (V != 0) {
-            u32 q = (V == 0xffffffffu) ? 1u : U / (V + 1u);
-            q = q ? q : 1u;                                          // ru >= rv
-            hg_step(ru, mu, rv, mv, q);
-        } else {
-            // rare (a partial quotient of 32 bits or more): work with v shifted left by whole words, as long as
-            // the shifted remainder keeps at least 33 bits of distance to ru (then 2^32 x <= ru still holds)
-            u32 x[8], xm[5];
-#pragma unroll
-            for (int i = 0; i < 8; i++) x[i] = rv[i];
-#pragma unroll
-            for (int i = 0; i < 5; i++) xm[i] = mv[i];
-            const int lu = hg_bitlen8(ru);
+        // leading 32 bits of ru and the aligned bits of rv (ru >= rv >= 2^96 here)
+        const int lu = hg_bitlen8(ru);
+        const int s = lu - 32;
+        const u32 X = hg_extract32(ru, s), Y = hg_extract32(rv, s);
+        u32 a = 1, b = 0, c = 0, d = 1, x = X, y = Y;
+        int k = 0;
+        if (big) {
+            // Euclid on (x, y):  x_k = (-1)^k (a X - b Y),  y_k = (-1)^(k+1) (c X - d Y)
+            const u32 ylim = s < 112 ? (1u << (128 - s)) : 0x10000u; // stay above 2^128 / keep 16 significant bits
 #pragma unroll 1
-            while (hg_bitlen8(x) + 33 <= lu) {
-#pragma unroll
-                for (int i = 7; i > 0; i--) x[i] = x[i - 1];
-                x[0] = 0;
-#pragma unroll
-                for (int i = 4; i > 0; i--) xm[i] = xm[i - 1];
-                xm[0] = 0;
+            while (y >= ylim) {
+                const u32 q = x / y, r = x - q * y;
+                if (r < ylim || q >= 0x10000u) break;
+                const u32 c2 = a + q * c, d2 = b + q * d;            // a, b, c, d, q < 2^16: no overflow
+                if (c2 >= 0x10000u || d2 >= 0x10000u) break;
+                a = c; b = d; c = c2; d = d2;
+                x = y; y = r;
+                k++;
             }
-            const u32 V2 = (u32)((hg_top2(x, h) << c) >> 32);
-            u32 q = (V2 == 0xffffffffu) ? 1u : U / (V2 + 1u);
-            q = q ? q : 1u;
-            hg_step(ru, mu, x, xm, q);
         }
-        // keep ru >= rv
-        u32 borrow = 0;
+        if (k > 0) {
+            // u' = +-(a u - b v), v' = +-(d v - c u): the sign that makes the remainder non-negative (for an odd
+            // number of steps both come out negative; an overshooting approximation can flip one more)
+            u32 nu[8], nv[8], mu[6], mv[6];
+            hg_lin<8>(nu, ru, a, rv, b);
+            hg_lin<6>(mu, bu, a, bv, b);
+            hg_lin<8>(nv, rv, d, ru, c);
+            hg_lin<6>(mv, bv, d, bu, c);
+            if (nu[7] >> 31) { hg_neg<8>(nu); hg_neg<6>(mu); }
+            if (nv[7] >> 31) { hg_neg<8>(nv); hg_neg<6>(mv); }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const u64 d = (u64)ru[i] - rv[i] - borrow;
-            borrow = (u32)(d >> 63);
+            for (int i = 0; i < 8; i++) { ru[i] = nu[i]; rv[i] = nv[i]; }
+#pragma unroll
+            for (int i = 0; i < 6; i++) { bu[i] = mu[i]; bv[i] = mv[i]; }
+        } else {
+            // one step u -= q 2^(32 j) v with 1 <= q 2^(32 j) <= floor(ru / rv): v is shifted left by whole words while
+            // it keeps at least 33 bits of distance to ru (then 2^32 x <= ru still holds)
+            u32 xr[8], xb[6];
+#pragma unroll
+            for (int i = 0; i < 8; i++) xr[i] = rv[i];
+#pragma unroll
+            for (int i = 0; i < 6; i++) xb[i] = bv[i];
+            u32 V = Y;
+            if (V == 0) {
+#pragma unroll 1
+                while (hg_bitlen8(xr) + 33 <= lu) {
+#pragma unroll
+                    for (int i = 7; i > 0; i--) xr[i] = xr[i - 1];
+                    xr[0] = 0;
+#pragma unroll
+                    for (int i = 5; i > 0; i--) xb[i] = xb[i - 1];
+                    xb[0] = 0;
+                }
+                V = hg_extract32(xr, s);
+            }
+            u32 q = (V == 0xffffffffu) ? 1u : X / (V + 1u);
+            q = q ? q : 1u;                                          // ru >= rv
+            hg_lin<8>(ru, ru, 1u, xr, q);
+            hg_lin<6>(bu, bu, 1u, xb, q);
         }
-        if (borrow) {
+        if (hg_less8(ru, rv)) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) { const u32 y = ru[i]; ru[i] = rv[i]; rv[i] = y; }
+            for (int i = 0; i < 8; i++) { const u32 z = ru[i]; ru[i] = rv[i]; rv[i] = z; }
 #pragma unroll
-            for (int i = 0; i < 5; i++) { const u32 y = mu[i]; mu[i] = mv[i]; mv[i] = y; }
-            sv ^= 1u;
+            for (int i = 0; i < 6; i++) { const u32 z = bu[i]; bu[i] = bv[i]; bv[i] = z; }
         }
     }
     if (fallback) {
@@ -147,9 +191,10 @@ EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8]) {
         for (int i = 0; i < 8; i++) { rho_abs[i] = (i == 0) ? 1u : 0u; tau[i] = t[i]; }
         rho_neg = 0;
     } else {
+        rho_neg = bv[5] >> 31;
+        if (rho_neg) hg_neg<6>(bv);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { rho_abs[i] = (i < 5) ? mv[i] : 0u; tau[i] = rv[i]; }
-        rho_neg = sv;
+        for (int i = 0; i < 8; i++) { rho_abs[i] = (i < 6) ? bv[i] : 0u; tau[i] = rv[i]; }
     }
 }
 
