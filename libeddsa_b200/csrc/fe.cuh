@@ -89,6 +89,9 @@ EDG_HD void fe_copy(fe &r, const fe &a) {
 // ---------------------------------------------------------------------------------------------------
 // carry-chain primitives
 // ---------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+static __constant__ u32 c_fe_zero = 0;        // a zero the compiler cannot see through (see EDG_CATCH64)
+#endif
 #if defined(__CUDA_ARCH__)
 
 // r = a + b over 8 words, returns the carry out (0 / 1)
@@ -135,27 +138,40 @@ __device__ __forceinline__ u32 subw8(u32 r[8], u32 x) {
 // hardware carry chain; the carry out lands in acc[2 CNT].  (IMAD.WIDE.U32 / IMAD.WIDE.U32.X in SASS.)
 template <int CNT> __device__ __forceinline__ void cmad(u32 *acc, const u32 *a, u32 bi);
 template <> __device__ __forceinline__ void cmad<0>(u32 *, const u32 *, u32) {}
+// The carry out is caught as a 64-bit value (carry, 0) written to the FRESH pair acc[2 CNT], acc[2 CNT + 1] (every
+// caller's carry word is untouched so far): the next row uses that pair as the addend of its top product, and a
+// 64-bit result lands in an aligned register pair without a separate zeroing move.
+#define EDG_CATCH64(acc, k) { acc[k] = c64; acc[(k) + 1] = c64 & c_fe_zero; }   /* zero high word made on the ALU pipe (ptxas would zero it with IMAD.MOV on the multiplier pipe) */
 template <> __device__ __forceinline__ void cmad<1>(u32 *acc, const u32 *a, u32 bi) {
-    asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, %2, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]) : "r"(a[0]), "r"(bi));
+    u32 c64;
+    asm("mad.lo.cc.u32 %0, %3, %4, %0; madc.hi.cc.u32 %1, %3, %4, %1; addc.u32 %2, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "=r"(c64) : "r"(a[0]), "r"(bi));
+    EDG_CATCH64(acc, 2)
 }
 template <> __device__ __forceinline__ void cmad<2>(u32 *acc, const u32 *a, u32 bi) {
-    asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1; madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3; addc.u32 %4, %4, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]) : "r"(a[0]), "r"(a[2]), "r"(bi));
+    u32 c64;
+    asm("mad.lo.cc.u32 %0, %5, %7, %0; madc.hi.cc.u32 %1, %5, %7, %1; madc.lo.cc.u32 %2, %6, %7, %2; madc.hi.cc.u32 %3, %6, %7, %3; addc.u32 %4, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "=r"(c64) : "r"(a[0]), "r"(a[2]), "r"(bi));
+    EDG_CATCH64(acc, 4)
 }
 template <> __device__ __forceinline__ void cmad<3>(u32 *acc, const u32 *a, u32 bi) {
+    u32 c64;
     asm("mad.lo.cc.u32 %0, %7, %10, %0; madc.hi.cc.u32 %1, %7, %10, %1; madc.lo.cc.u32 %2, %8, %10, %2; madc.hi.cc.u32 %3, %8, %10, %3; "
-        "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5; addc.u32 %6, %6, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6])
+        "madc.lo.cc.u32 %4, %9, %10, %4; madc.hi.cc.u32 %5, %9, %10, %5; addc.u32 %6, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "=r"(c64)
         : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(bi));
+    EDG_CATCH64(acc, 6)
 }
 template <> __device__ __forceinline__ void cmad<4>(u32 *acc, const u32 *a, u32 bi) {
+    u32 c64;
     asm("mad.lo.cc.u32 %0, %9, %13, %0; madc.hi.cc.u32 %1, %9, %13, %1; madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3; "
         "madc.lo.cc.u32 %4, %11, %13, %4; madc.hi.cc.u32 %5, %11, %13, %5; madc.lo.cc.u32 %6, %12, %13, %6; madc.hi.cc.u32 %7, %12, %13, %7; "
-        "addc.u32 %8, %8, 0;"
-        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "+r"(acc[8])
+        "addc.u32 %8, 0, 0;"
+        : "+r"(acc[0]), "+r"(acc[1]), "+r"(acc[2]), "+r"(acc[3]), "+r"(acc[4]), "+r"(acc[5]), "+r"(acc[6]), "+r"(acc[7]), "=r"(c64)
         : "r"(a[0]), "r"(a[2]), "r"(a[4]), "r"(a[6]), "r"(bi));
+    EDG_CATCH64(acc, 8)
 }
+#undef EDG_CATCH64
 
 // Same rows WITHOUT the carry-out word: for use when the top 64-bit slot of the row is "fresh" (it holds
 // at most the 0/1 carry caught from an earlier row), because then  a*b + slot + carry-in
