@@ -11,11 +11,19 @@ using namespace edg;
 #ifndef EDG_VERIFY_WAVES
 #define EDG_VERIFY_WAVES 4  /* waves of resident threads per pass: sizes the per-signature records in scratch */
 #endif
+#ifndef EDG_VTHREADS
+#define EDG_VTHREADS EDG_THREADS   /* block size of the window-loop kernel */
+#endif
+#ifndef EDG_LB_VLOOP
+#define EDG_LB_VLOOP EDG_LB_VERIFY_
+#endif
 #ifndef EDG_LB_VERIFY
-#define EDG_LB_VERIFY 4     /* min resident blocks per SM the register allocator must allow: 128 registers, 4 warps/SMSP
+#define EDG_LB_VERIFY 4     /* front kernel: min resident blocks per SM the register allocator must allow: 128 registers, 4 warps/SMSP
                                (measured +4 % over 3 blocks, profiles/r01_summary.md) */
 #endif
+#define EDG_LB_VERIFY_ EDG_LB_VERIFY
 namespace {
+constexpr int kVThreads = EDG_VTHREADS;
 
 // stage 1: one signature per thread -> its EDG_VSTATE_WORDS-word record
 __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t n, size_t first, const uint8_t *sig, const uint8_t *pub,
@@ -31,7 +39,7 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t
 
 // stage 2: the window loop.  Whole warps stay together (the trip count is agreed per warp with a full-mask
 // reduction): lanes past the end redo the last record and drop the result.
-__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify(size_t n, uint8_t *ok, const u32 *state, const u32 *__restrict__ wtab) {
+__global__ void __launch_bounds__(kVThreads, EDG_LB_VLOOP) k_verify(size_t n, uint8_t *ok, const u32 *state, const u32 *__restrict__ wtab) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ((k & ~(size_t)31) >= n) return;
     const size_t kk = k < n ? k : n - 1;
@@ -68,8 +76,8 @@ extern "C" {
 // signatures per pass: a whole number of waves of the loop kernel (resident threads of the device)
 static size_t verify_chunk(int sm_count) {
     int bps = 0;
-    grid_for(k_verify, (size_t)1 << 40, 0, sm_count, &bps);
-    return (size_t)sm_count * bps * kThreads * EDG_VERIFY_WAVES;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_verify, kVThreads, 0) != cudaSuccess || bps < 1) bps = 1;
+    return (size_t)sm_count * bps * kVThreads * EDG_VERIFY_WAVES;
 }
 
 size_t edg_verify_scratch_bytes(int sm_count) { return verify_chunk(sm_count) * EDG_VSTATE_WORDS * sizeof(u32); }
@@ -98,9 +106,8 @@ int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *
     const size_t chunk = verify_chunk(sm_count);
     for (size_t first = 0; first < n; first += chunk) {
         const size_t m = n - first < chunk ? n - first : chunk;
-        const unsigned blocks = (unsigned)((m + kThreads - 1) / kThreads);
-        k_verify_front<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch);
-        k_verify<<<blocks, kThreads, 0, (cudaStream_t)stream>>>(m, ok + first, (const u32 *)scratch, (const u32 *)table);
+        k_verify_front<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch);
+        k_verify<<<(unsigned)((m + kVThreads - 1) / kVThreads), kVThreads, 0, (cudaStream_t)stream>>>(m, ok + first, (const u32 *)scratch, (const u32 *)table);
     }
     return (int)cudaGetLastError();
 }

@@ -54,7 +54,7 @@ def ed25519_kat():
 
 def verify_adv():
     """(sig, pub, [msg], cls, expect) adversarial rows; expect = decision of the compiled reference."""
-    a = _load("verify_adv.bin", 228)
+    a = np.concatenate([_load("verify_adv.bin", 228), _load("verify_torsion.bin", 228)])   # + mixed-order A and R rows
     lens = a[:, 96].astype(np.int64) | (a[:, 97].astype(np.int64) << 8)
     msgs = [a[i, 100:100 + lens[i]].tobytes() for i in range(len(a))]
     return a[:, :64].copy(), a[:, 64:96].copy(), msgs, a[:, 98].copy(), a[:, 99].copy()
