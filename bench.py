@@ -14,7 +14,10 @@ reported under "also" (each with its own integer-multiply roofline fraction).
   e2e       same metric through the public host-buffer C-ABI (ed25519_verify_batch) from pinned host
             memory: H2D of sig/pub/msg and D2H of the accept flags inside the timed region
   roofline  compute-bound on the 32x32->64 integer multiplier (IMAD.WIDE, fmaheavy pipe); peak measured
-            on this pool's B200s (profiles/r01_pipe_microbench.md): 32 wide multiplies/clk/SM
+            on this pool's B200s (profiles/r01_pipe_microbench.md): 32 wide multiplies/clk/SM.  "frac" counts the
+            field work the engine EXECUTES (half-size scalars: ~133 k wide multiplies per signature),
+            "frac_reference_fm" the field work the reference's algorithm would need (232 k) at our rate —
+            that one can exceed 1 because the algorithm, not the pipe, got faster
   cpu_baseline  the UNMODIFIED reference (oracle/_ref, kind "reference"; oracle port otherwise) on the
             box's host cores, one instance per core, bounded sample of the same workload
 One process per GPU; batches are sharded by rank (no collective on the data path); the timed region
@@ -330,14 +333,17 @@ def run_ours(args):
         achieved = per_gpu * products(OURS_FM["verify"]) / 1e12
         roofline = {
             "bound": "int32-multiply (IMAD.WIDE on the fmaheavy pipe; compute-bound, see DESIGN.md §4)",
-            "kernel": "k_verify",
+            "kernel": "k_verify_front + k_verify (one pass = %d launches: the two stages per chunk of signatures)" % max(int(launches) // K, 1),
             "achieved": achieved, "peak": PEAK_TMULS, "unit": "T wide-multiplies/s (32x32->64)", "frac": achieved / PEAK_TMULS,
             "frac_reference_fm": per_gpu * products(REF_FM["verify"]) / 1e12 / PEAK_TMULS,
             "peak_source": "measured: tools/pipe_bench.cu on this pool's B200 = 32 IMAD.WIDE/clk/SM x 148 SM x 1965 MHz (profiles/r01_pipe_microbench.md)",
             "wide_multiplies_per_op_executed": products(OURS_FM["verify"]),
             "wide_multiplies_per_op_reference_fm": products(REF_FM["verify"]),
             "kernel_ms_per_launch": kernel_ms,
-            "traffic": None,
+            "traffic": ncu_traffic(n),
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of both stages from the ncu --set full capture on 2^18 signatures "
+                            "(profiles/r01_ncu_summary.json), scaled to this batch; ~7 KB/signature = the 2.4 KB record the front stage "
+                            "hands to the window loop (two 8-entry point tables), written once and read back ~2x: 5 % of HBM bandwidth",
             "hbm": {"algorithmic_bytes_per_launch": n * IO_BYTES["verify"],
                     "achieved_gbs": n * IO_BYTES["verify"] / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak(),
                     "note": "HBM is not the bound: <0.1 % of measured copy bandwidth"},
@@ -367,6 +373,16 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic(n):
+    """DRAM bytes per pass over n signatures, from the committed ncu capture (None if it is not there)."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        per_op = sum(d[k]["dram_read_bytes"] + d[k]["dram_write_bytes"] for k in ("verify_loop", "verify_front")) / d["ops_per_launch"]
+        return int(per_op * n)
+    except Exception:
+        return None
 
 
 def hbm_peak():

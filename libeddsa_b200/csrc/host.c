@@ -28,6 +28,7 @@
 
 #define EDG_MAX_DEV 16
 #define EDG_NSLOT 3
+#define EDG_VERIFY_WAVES_HINT 4 /* a verify pass is this many waves of resident threads (kernels_verify.cu: EDG_VERIFY_WAVES) */
 #define EDG_ALIGN 256
 #define EDG_MAX_USER_STREAMS 16
 
@@ -52,6 +53,9 @@ typedef struct {
     pthread_mutex_t lock; /* the host-buffer pipeline of this device is exclusive */
     cudaStream_t stream[EDG_NSLOT];
     cudaEvent_t done[EDG_NSLOT];
+    cudaStream_t kstream;                       /* verify: all kernels of the host-buffer pipeline run here, one after the other */
+    cudaEvent_t in_ready[EDG_NSLOT], k_done[EDG_NSLOT];
+    size_t verify_pass;                         /* signatures per pass of the two verify kernels (whole waves) */
     uint8_t *h_in[EDG_NSLOT], *h_out[EDG_NSLOT];
     uint8_t *d_in[EDG_NSLOT], *d_out[EDG_NSLOT];
     size_t in_cap, out_cap;
@@ -147,7 +151,11 @@ static int dev_basic(int dev, edg_dev_t **out_ctx)
             for (i = 0; i < EDG_NSLOT; i++) {
                 CU(cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking));
                 CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&c->in_ready[i], cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&c->k_done[i], cudaEventDisableTiming));
             }
+            CU(cudaStreamCreateWithFlags(&c->kstream, cudaStreamNonBlocking));
+            c->verify_pass = c->scratch_bytes / edg_verify_record_bytes();
             CU(cudaMalloc(&c->wtab, edg_verify_table_bytes()));
             rc = edg_verify_table_init(c->wtab, c->stream[0]);
             if (rc) { rc = fail(rc, "window table build failed: %s", cudaGetErrorString((cudaError_t)rc)); goto out; }
@@ -197,7 +205,7 @@ static int dev_reserve(edg_dev_t *c, size_t in_need, size_t out_need, int need_s
         c->out_cap = out_need;
     }
     if (need_scratch && !c->scratch[0])
-        for (i = 0; i < EDG_NSLOT; i++) CU(cudaMalloc(&c->scratch[i], c->scratch_bytes));
+        CU(cudaMalloc(&c->scratch[0], c->scratch_bytes));      /* one slab: the pipeline's verify kernels run one after the other */
 out:
     return rc;
 }
@@ -266,12 +274,17 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
     /* aim for >= 4 chunks per shard (copy/compute overlap) but never tiny ones */
     target = (nshard + 3) / 4;
     if (target < 65536) target = 65536;
+    /* verify: chunks of whole passes of its two kernels (whole waves of resident threads), kernels serialised on one
+     * stream so that the two stages never share an SM (instruction cache) while copies overlap on the slot streams */
+    if (j->op == OP_VERIFY && nshard > c->verify_pass) target = c->verify_pass;
     if (target > nshard) target = nshard;
     for (pos = lo; pos < hi;) {
         size_t m = target, in_bytes, out_bytes, ofs;
         uint8_t *d_in[3] = {NULL, NULL, NULL};
         const uint8_t *d_msgs = NULL;
         const unsigned long long *d_off = NULL;
+        /* verify: a short first chunk (one wave) so that the kernels start early; its copy is the only exposed one */
+        if (j->op == OP_VERIFY && chunk_no == 0 && target == c->verify_pass && c->verify_pass >= 8) m = c->verify_pass / EDG_VERIFY_WAVES_HINT;
         if (pos + m > hi) m = hi - pos;
         /* shrink the chunk until it fits the staging budget (ragged messages); a single oversized item grows the buffers */
         while (m > 1 && chunk_in_bytes(j, pos, pos + m) > g_chunk_bytes) m = (m + 1) / 2;
@@ -321,8 +334,17 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
             }
             d_msgs = c->d_in[s] + ofs;
         }
-        rc = launch(c, j->op, m, c->d_out[s], d_in, d_msgs, d_off, j->fixed_len, c->scratch[s], c->stream[s]);
-        if (rc) goto out;
+        if (j->op == OP_VERIFY) {
+            CU(cudaEventRecord(c->in_ready[s], c->stream[s]));
+            CU(cudaStreamWaitEvent(c->kstream, c->in_ready[s], 0));
+            rc = launch(c, j->op, m, c->d_out[s], d_in, d_msgs, d_off, j->fixed_len, c->scratch[0], c->kstream);
+            if (rc) goto out;
+            CU(cudaEventRecord(c->k_done[s], c->kstream));
+            CU(cudaStreamWaitEvent(c->stream[s], c->k_done[s], 0));
+        } else {
+            rc = launch(c, j->op, m, c->d_out[s], d_in, d_msgs, d_off, j->fixed_len, NULL, c->stream[s]);
+            if (rc) goto out;
+        }
         CU(cudaMemcpyAsync(pin_out ? j->out + pos * j->out_item : c->h_out[s], c->d_out[s], m * j->out_item,
                            cudaMemcpyDeviceToHost, c->stream[s]));
         CU(cudaEventRecord(c->done[s], c->stream[s]));
@@ -583,9 +605,12 @@ void eddsa_b200_shutdown(void)
             c->scratch[i] = NULL;
             cudaStreamDestroy(c->stream[i]);
             cudaEventDestroy(c->done[i]);
+            cudaEventDestroy(c->in_ready[i]);
+            cudaEventDestroy(c->k_done[i]);
         }
         for (i = 0; i < EDG_MAX_USER_STREAMS; i++)
             if (c->user_scratch[i].used) { cudaFree(c->user_scratch[i].buf); c->user_scratch[i].used = 0; }
+        cudaStreamDestroy(c->kstream);
         if (c->wtab) cudaFree(c->wtab);
         c->wtab = NULL;
         c->in_cap = c->out_cap = 0;

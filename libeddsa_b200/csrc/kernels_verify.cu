@@ -80,6 +80,8 @@ static size_t verify_chunk(int sm_count) {
     return (size_t)sm_count * bps * kVThreads * EDG_VERIFY_WAVES;
 }
 
+size_t edg_verify_record_bytes(void) { return EDG_VSTATE_WORDS * sizeof(u32); }
+
 size_t edg_verify_scratch_bytes(int sm_count) { return verify_chunk(sm_count) * EDG_VSTATE_WORDS * sizeof(u32); }
 
 size_t edg_verify_table_bytes(void) { return (2 * (size_t)EDG_WTAB_WORDS + 48) * sizeof(u32); }
