@@ -5,6 +5,7 @@
 // Public data only, so table lookups are direct-indexed.
 // Also hosts pk_ed25519_to_x25519 (it shares the decompression).
 // Replaces ed25519_verify / pk_ed25519_to_x25519: /root/reference/lib/ed25519-sha512.c:148-237.
+#define EDG_SHA_MSGWORD_NOINLINE
 #include "kernel_common.cuh"
 using namespace edg;
 

@@ -426,18 +426,16 @@ EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, con
 #pragma unroll
     for (int i = 0; i < 8; i++) { state[576 + i] = et[i]; state[584 + i] = er[i]; state[592 + i] = es[i]; }
 
-    // tables of Q = -sign(rho) A and P = -R'                                                      :151, :174-175
-    u32 good;
-    {
+    // tables of Q = -sign(rho) A and P = -R' (one loop body for both points: half the code)        :151, :174-175
+    u32 good = 0xffffffffu;
+#pragma unroll 1
+    for (int which = 0; which < 2; which++) {
         ge_p3 Q;
         u32 a[8], canon;
-        load_words8(a, pub);
-        good = ge_frombytes(Q, a, rho_neg == 0);
-        ge_cached_table(state, Q);
-        load_words8(a, sig);
-        good &= ge_frombytes(Q, a, true, &canon);
-        good &= canon;
-        ge_cached_table(state + 288, Q);
+        load_words8(a, which ? sig : pub);
+        good &= ge_frombytes(Q, a, which ? true : (rho_neg == 0), &canon);
+        good &= which ? canon : 0xffffffffu;              // only R has to be canonical (Q2); any encoding of A is accepted (Q3)
+        ge_cached_table(state + 288 * which, Q);
     }
     state[600] = good & 1u;
     state[601] = (u32)nwin;

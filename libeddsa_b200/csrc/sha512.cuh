@@ -81,7 +81,14 @@ EDG_NOINLINE void sha512_compress(u64 h[8], u64 w[16]) {
 
 // The 8-byte big-endian word at message offset m of the PADDED message (0x80 after the last byte,
 // zeros elsewhere; the length field is patched in by the caller).
+// Inlined 32 times this helper is most of the hash's code; the verify kernels (public data only) call it
+// out of line to keep their instruction footprint small, the secret-key kernels keep it inline so that no
+// secret-holding register is ever saved to the stack around a call.
+#if defined(EDG_SHA_MSGWORD_NOINLINE) && defined(__CUDACC__)
+static __host__ __device__ __noinline__ u64 sha512_msg_word(const uint8_t *msg, u64 len, u64 m) {
+#else
 EDG_HD u64 sha512_msg_word(const uint8_t *msg, u64 len, u64 m) {
+#endif
     if (m + 8 <= len) {
         const uint8_t *p = msg + m;
         if ((((uintptr_t)p) & 7) == 0) {
