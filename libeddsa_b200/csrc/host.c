@@ -155,7 +155,7 @@ static int dev_basic(int dev, edg_dev_t **out_ctx)
                 CU(cudaEventCreateWithFlags(&c->k_done[i], cudaEventDisableTiming));
             }
             CU(cudaStreamCreateWithFlags(&c->kstream, cudaStreamNonBlocking));
-            c->verify_pass = c->scratch_bytes / edg_verify_record_bytes();
+            c->verify_pass = (c->scratch_bytes - 256) / edg_verify_record_bytes();
             CU(cudaMalloc(&c->wtab, edg_verify_table_bytes()));
             rc = edg_verify_table_init(c->wtab, c->stream[0]);
             if (rc) { rc = fail(rc, "window table build failed: %s", cudaGetErrorString((cudaError_t)rc)); goto out; }

@@ -393,52 +393,64 @@ EDG_HD int sc_digit16(const u32 *e, int j) { return (int)((e[j >> 3] >> (4 * (j 
 //   loop : the window loop and the projective comparison with the neutral element
 // record: [0, 288) table of Q = -sign(rho) A, [288, 576) table of P = -R' (9 cached points x 32 words each),
 //         [576, 584) tau, [584, 592) |rho|, [592, 600) rho S recoded to signed 16-bit digits, [600] flags
-//         (bit 0: both points decoded and the R bytes are canonical), [601] windows needed.
+//         (bit 0: both points decoded and the R bytes are canonical), [601] windows needed, [602] index of the
+//         signature within its pass (records are not stored in input order).
 #define EDG_VSTATE_WORDS 608
 
-EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
-    u32 et[8], er[8], es[8], rho_neg;
-    {
-        // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
-        u64 pre[8], st[8];
-        u32 h[16], t[8], s[8];
-        load_words8(t, sig);
-        load_words8(h, pub);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            pre[k] = be64_from_le_words(t[2 * k], t[2 * k + 1]);
-            pre[4 + k] = be64_from_le_words(h[2 * k], h[2 * k + 1]);
-        }
-        sha512_prefixed<8>(st, pre, msg, len);
-        sha512_state_to_le_words(h, st);
-        sc_reduce512(t, h);
-        half_gcd(er, rho_neg, et, t);                     // er = |rho|, et = tau
-        load_words8(h, sig + 8);
-        sc_reduce256(s, h);                               // no range check on S (Q1)               :163
-#pragma unroll
-        for (int i = 0; i < 8; i++) h[i] = 0;
-        sc_muladd(es, er, s, h);                          // |rho| S mod L
-        sc_recode_window(es);
-    }
-    const int bt = hg_bitlen8(et), br = hg_bitlen8(er);
-    int nwin = ((bt > br ? bt : br) + 5) >> 2;
-    nwin = nwin < 32 ? 32 : nwin;                         // all 16-bit windows of rho S sit below bit 128
-#pragma unroll
-    for (int i = 0; i < 8; i++) { state[576 + i] = et[i]; state[584 + i] = er[i]; state[592 + i] = es[i]; }
+// front, part 1: the three scalars.  Returns the number of windows this signature needs; the caller then picks the
+// record (kernels: records are handed out sorted by window count, so that the lanes of a warp of the loop kernel
+// agree on their trip count) and calls part 2.
+struct verify_scalars { u32 et[8], er[8], es[8], rho_neg; };
 
-    // tables of Q = -sign(rho) A and P = -R' (one loop body for both points: half the code)        :151, :174-175
+EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
+    // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
+    u64 pre[8], st[8];
+    u32 h[16], t[8], s[8];
+    load_words8(t, sig);
+    load_words8(h, pub);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        pre[k] = be64_from_le_words(t[2 * k], t[2 * k + 1]);
+        pre[4 + k] = be64_from_le_words(h[2 * k], h[2 * k + 1]);
+    }
+    sha512_prefixed<8>(st, pre, msg, len);
+    sha512_state_to_le_words(h, st);
+    sc_reduce512(t, h);
+    half_gcd(v.er, v.rho_neg, v.et, t);                   // er = |rho|, et = tau
+    load_words8(h, sig + 8);
+    sc_reduce256(s, h);                                   // no range check on S (Q1)               :163
+#pragma unroll
+    for (int i = 0; i < 8; i++) h[i] = 0;
+    sc_muladd(v.es, v.er, s, h);                          // |rho| S mod L
+    sc_recode_window(v.es);
+    const int bt = hg_bitlen8(v.et), br = hg_bitlen8(v.er);
+    int nwin = ((bt > br ? bt : br) + 5) >> 2;
+    return nwin < 32 ? 32 : nwin;                         // all 16-bit windows of rho S sit below bit 128
+}
+
+// front, part 2: fill the record — scalars, the tables of Q = -sign(rho) A and P = -R', flags.   :151, :174-175
+EDG_HD void ed25519_verify_front_points(u32 *state, const verify_scalars &v, int nwin, u32 index, const u32 *sig, const u32 *pub) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) { state[576 + i] = v.et[i]; state[584 + i] = v.er[i]; state[592 + i] = v.es[i]; }
     u32 good = 0xffffffffu;
 #pragma unroll 1
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 2; which++) {             // one loop body for both points: half the code
         ge_p3 Q;
         u32 a[8], canon;
         load_words8(a, which ? sig : pub);
-        good &= ge_frombytes(Q, a, which ? true : (rho_neg == 0), &canon);
+        good &= ge_frombytes(Q, a, which ? true : (v.rho_neg == 0), &canon);
         good &= which ? canon : 0xffffffffu;              // only R has to be canonical (Q2); any encoding of A is accepted (Q3)
         ge_cached_table(state + 288 * which, Q);
     }
     state[600] = good & 1u;
     state[601] = (u32)nwin;
+    state[602] = index;
+}
+
+EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
+    verify_scalars v;
+    const int nwin = ed25519_verify_front_scalars(v, sig, pub, msg, len);
+    ed25519_verify_front_points(state, v, nwin, 0, sig, pub);
 }
 
 EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab) {
