@@ -5,7 +5,7 @@
 using namespace edg;
 
 #ifndef EDG_LB_X25519
-#define EDG_LB_X25519 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#define EDG_LB_X25519 4     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
 #endif
 namespace {
 

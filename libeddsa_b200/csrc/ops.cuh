@@ -68,38 +68,49 @@ EDG_HD void x25519_front(fe &x2, fe &z2, const u32 scalar[8], const u32 point[8]
     fe_from_words(x1, point);                             // all 256 bits, bit 255 -> +19 (Q6)   x25519.c:142
     fe_set_u32(x2, 1); fe_set_u32(z2, 0);                 // (1 : 0)                              x25519.c:111-112
     fe_copy(x3, x1); fe_set_u32(z3, 1);                   // (u : 1)
-    // 256 steps, most significant bit first (bit 255 is always 0 after clamping, kept for fidelity)
+    // 256 steps, most significant bit first (bit 255 is always 0 after clamping, kept for fidelity).  The reference
+    // swaps before AND after every step (x25519.c:118-120); the swap after step i and the swap before step i-1
+    // merge into one conditional swap by (bit_i xor bit_{i-1}).  Bits 2..0 are zero after clamping, so the last
+    // three steps are pure doublings of (x2 : z2) — their differential additions would never be read.
+    u32 prev = 0;
 #pragma unroll 1
     for (int pos = 255; pos >= 0; pos--) {
         // bit `pos` = top bit of e[7]; then shift the whole scalar left by one (no indexed access)
-        const u32 mask = ct_mask(0u - (e[7] >> 31));
+        const u32 bit = e[7] >> 31;
+        const u32 mask = ct_mask(0u - (bit ^ prev));
+        prev = bit;
 #pragma unroll
         for (int i = 7; i > 0; i--) e[i] = (e[i] << 1) | (e[i - 1] >> 31);
         e[0] <<= 1;
         fe_cswap(x2, x3, mask);
         fe_cswap(z2, z3, mask);
-        fe sa, da, aa, bb, ee, sb, db, t1, t2;
+        fe sa, da, aa, bb, ee, t1;
         fe_add(sa, x2, z2);
         fe_sub(da, x2, z2);
         fe_sq(aa, sa);
         fe_sq(bb, da);
-        fe_add(sb, x3, z3);
-        fe_sub(db, x3, z3);
-        fe_mul(x2, aa, bb);                               // x2' = AA BB
-        fe_sub(ee, aa, bb);                               // E = AA - BB   (3)
+        if (pos >= 3) {                                       // public loop position, not data
+            fe sb, db, t2;
+            fe_add(sb, x3, z3);
+            fe_sub(db, x3, z3);
+            fe_mul(t1, da, sb);                               // DA
+            fe_mul(t2, db, sa);                               // CB
+            fe_add(x3, t1, t2);
+            fe_sq(x3, x3);                                    // x3' = (DA + CB)^2
+            fe_sub(t1, t1, t2);
+            fe_sq(t1, t1);
+            fe_mul(z3, t1, x1);                               // z3' = x1 (DA - CB)^2
+        }
+        fe_mul(x2, aa, bb);                                   // x2' = AA BB
+        fe_sub(ee, aa, bb);                                   // E = AA - BB
         fe_mul121665(t1, ee);
-        fe_add(t1, t1, aa);                               // AA + 121665 E (2)
-        fe_mul(z2, ee, t1);                               // z2' = E (AA + a24 E)
-        fe_mul(t1, da, sb);                               // DA
-        fe_mul(t2, db, sa);                               // CB
-        fe_add(x3, t1, t2);
-        fe_sq(x3, x3);                                    // x3' = (DA + CB)^2
-        fe_sub(t1, t1, t2);
-        fe_sq(t1, t1);
-        fe_mul(z3, t1, x1);                               // z3' = x1 (DA - CB)^2
-        fe_cswap(x2, x3, mask);
-        fe_cswap(z2, z3, mask);
+        fe_add(t1, t1, aa);                                   // AA + 121665 E
+        fe_mul(z2, ee, t1);                                   // z2' = E (AA + a24 E)
     }
+    // bit 0 is zero after clamping: the last pending swap is the identity, applied anyway (mask from data)
+    const u32 mask = ct_mask(0u - prev);
+    fe_cswap(x2, x3, mask);
+    fe_cswap(z2, z3, mask);
 }
 
 // back: out = x2 * zinv, canonical bytes                                                          x25519.c:147-149
