@@ -72,16 +72,16 @@ EDG_HD void x25519_front(fe &x2, fe &z2, const u32 scalar[8], const u32 point[8]
     // swaps before AND after every step (x25519.c:118-120); the swap after step i and the swap before step i-1
     // merge into one conditional swap by (bit_i xor bit_{i-1}).  Bits 2..0 are zero after clamping, so the last
     // three steps are pure doublings of (x2 : z2) — their differential additions would never be read.
-    u32 prev = 0;
+    // The word of the scalar holding the next 32 bits is picked at a PUBLIC index (the loop position) every 32 steps
+    // and shifted out one bit per step (instead of shifting all eight words every step).
+    u32 prev = 0, cur = 0;
 #pragma unroll 1
     for (int pos = 255; pos >= 0; pos--) {
-        // bit `pos` = top bit of e[7]; then shift the whole scalar left by one (no indexed access)
-        const u32 bit = e[7] >> 31;
+        if ((pos & 31) == 31) cur = e[pos >> 5];
+        const u32 bit = cur >> 31;
+        cur <<= 1;
         const u32 mask = ct_mask(0u - (bit ^ prev));
         prev = bit;
-#pragma unroll
-        for (int i = 7; i > 0; i--) e[i] = (e[i] << 1) | (e[i - 1] >> 31);
-        e[0] <<= 1;
         fe_cswap(x2, x3, mask);
         fe_cswap(z2, z3, mask);
         fe sa, da, aa, bb, ee, t1;
