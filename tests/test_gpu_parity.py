@@ -242,6 +242,32 @@ def test_full_size_properties_2pow20(ed, cpu):
     assert (out[sample] == cpu.x25519(a[sample], pts[sample])).all()
 
 
+def test_verify_pass_boundaries(ed, cpu):
+    """The two verify kernels work in passes of whole waves (303 104 signatures on 148 SMs) and hand records out in
+    sorted order: batches one past a pass, with a ragged last warp, through the device API (one launch pair per
+    pass) and the host pipeline (short first chunk), every tenth signature corrupted, compared with the oracle on a
+    sample and by position (the corrupted ones, and only they, are rejected)."""
+    import torch
+    rng = np.random.default_rng(650)
+    n = 303_104 + 1 + 37
+    sec, msgs = rand_bytes(rng, n, 32), rand_bytes(rng, n, 64)
+    pub = ed.ed25519_genpub_batch(sec)
+    sig = ed.ed25519_sign_batch(sec, pub, msgs, fixed_len=64)
+    bad = np.zeros(n, bool)
+    bad[::10] = True
+    bad[[n - 1, n - 2, 303_103, 303_104]] = True
+    sig[bad, 7] ^= 0x10                                        # R changes: still a curve point or not, never the right one
+    dev = torch.device("cuda:0")
+    ok_t = torch.empty((n,), dtype=torch.uint8, device=dev)
+    ed.ed25519_verify_batch_dev(ok_t, torch.from_numpy(sig).to(dev), torch.from_numpy(pub).to(dev), torch.from_numpy(msgs).to(dev), fixed_len=64)
+    ok_dev = ok_t.cpu().numpy()
+    ok_host = ed.ed25519_verify_batch(sig, pub, msgs, fixed_len=64)
+    assert (ok_dev == ok_host).all()
+    assert (ok_host.astype(bool) == ~bad).all()
+    sample = np.concatenate([np.arange(n - 64, n), np.arange(303_040, n), rng.integers(0, n, 1500)])
+    assert (ok_host[sample] == cpu.verify(sig[sample], pub[sample], msgs[sample], fixed_len=64)).all()
+
+
 def test_verify_1kb_messages_with_corruption(ed, cpu):
     """Config 5 shape at a size the CPU can check: 1 KB messages, 10 % corrupted / non-canonical."""
     rng = np.random.default_rng(700)
