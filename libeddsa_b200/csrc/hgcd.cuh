@@ -112,8 +112,11 @@ EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8]) {
     for (int i = 0; i < 6; i++) { bu[i] = 0; bv[i] = 0; }
     bv[0] = 1;
     bool fallback = false;
+    // Every pass strictly decreases max(ru, rv) (a Lehmer pass by at least one bit), so ~130 passes suffice; the
+    // cap is a belt-and-braces bound so that no input can ever keep a GPU thread spinning.
 #pragma unroll 1
-    for (;;) {
+    for (int pass = 0;; pass++) {
+        if (pass >= 1024) { fallback = true; break; }
         const bool big = (rv[4] | rv[5] | rv[6] | rv[7]) != 0;      // rv >= 2^128: keep reducing
         if (!big) {
             if (bv[0] & 1u) break;                                   // odd rho: done
