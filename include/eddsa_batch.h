@@ -79,6 +79,10 @@ EDDSA_DECL unsigned long long eddsa_b200_launch_count(void);
  * 1 square, 2 add, 3 sub, 4 times 121665, 5 canonical form, 6 inverse, 7 power (p-5)/8, 8 negate);
  * a, b, out are n x 32 little-endian bytes, any 256-bit values.  Used by the GPU unit tests. */
 EDDSA_DECL int eddsa_b200_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op);
+/* diagnostic: copies the verify kernels' base-point window tables of the current device to `out`: table m (m = 0, 1)
+ * holds e * 2^(128 m) * B for e = 0 .. 2^15 as 96-byte entries (y+x, y-x, 2dxy; canonical little-endian field
+ * elements).  Returns the number of bytes written (2 x 32769 x 96) or 0 if `cap` is too small / on error. */
+EDDSA_DECL size_t eddsa_b200_verify_tables(uint8_t *out, size_t cap);
 /* human-readable description of the last error seen by the calling thread ("" if none) */
 EDDSA_DECL const char *eddsa_b200_last_error(void);
 

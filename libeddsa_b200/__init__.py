@@ -65,6 +65,7 @@ def lib():
             "pk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
             "sk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
             "eddsa_b200_fe_selftest": [sz, vp, vp, vp, ip],
+            "eddsa_b200_verify_tables": [vp, sz],
             "eddsa_b200_init": [],
             "eddsa_b200_device_count": [],
             "eddsa_b200_set_device_count": [ip],
@@ -74,6 +75,7 @@ def lib():
             fn.restype = ctypes.c_int
         L.eddsa_b200_shutdown.restype = None
         L.eddsa_b200_launch_count.restype = ctypes.c_ulonglong
+        L.eddsa_b200_verify_tables.restype = ctypes.c_size_t
         L.eddsa_b200_last_error.restype = ctypes.c_char_p
         L.ed25519_verify.restype = ctypes.c_bool
         L.ed25519_verify.argtypes = [vp, vp, vp, sz]
@@ -191,6 +193,15 @@ def sk_ed25519_to_x25519_batch(sk):
     sk = _arr(sk, 32, "sk")
     out = np.empty_like(sk)
     _check(lib().sk_ed25519_to_x25519_batch(len(sk), _p(out), _p(sk)), "sk_ed25519_to_x25519_batch")
+    return out
+
+
+def verify_tables():
+    """Diagnostic: the device-built window tables of B and 2^128 B as a (2, 32769, 3, 32) uint8 array."""
+    out = np.empty((2, 32769, 3, 32), np.uint8)
+    got = lib().eddsa_b200_verify_tables(_p(out), out.nbytes)
+    if got != out.nbytes:
+        raise EddsaB200Error(f"eddsa_b200_verify_tables returned {got}: " + lib().eddsa_b200_last_error().decode(errors="replace"))
     return out
 
 

@@ -14,6 +14,7 @@ extern "C" {
 int edg_fixedbase_init(void);
 size_t edg_verify_scratch_bytes(int sm_count);   /* = signatures per pass x edg_verify_record_bytes() */
 size_t edg_verify_record_bytes(void);
+unsigned edg_verify_waves(void);                  /* a pass = this many waves of resident threads of the loop kernel */
 int edg_launch_x25519(size_t n, uint8_t *out, const uint8_t *scalar, const uint8_t *point, int sm_count, void *stream);
 int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, int sm_count, void *stream);
 int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, int sm_count, void *stream);

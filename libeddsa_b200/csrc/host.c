@@ -28,7 +28,6 @@
 
 #define EDG_MAX_DEV 16
 #define EDG_NSLOT 3
-#define EDG_VERIFY_WAVES_HINT 4 /* a verify pass is this many waves of resident threads (kernels_verify.cu: EDG_VERIFY_WAVES) */
 #define EDG_ALIGN 256
 #define EDG_MAX_USER_STREAMS 16
 
@@ -284,7 +283,7 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
         const uint8_t *d_msgs = NULL;
         const unsigned long long *d_off = NULL;
         /* verify: a short first chunk (one wave) so that the kernels start early; its copy is the only exposed one */
-        if (j->op == OP_VERIFY && chunk_no == 0 && target == c->verify_pass && c->verify_pass >= 8) m = c->verify_pass / EDG_VERIFY_WAVES_HINT;
+        if (j->op == OP_VERIFY && chunk_no == 0 && target == c->verify_pass && c->verify_pass >= 8) m = c->verify_pass / edg_verify_waves();
         if (pos + m > hi) m = hi - pos;
         /* shrink the chunk until it fits the staging budget (ragged messages); a single oversized item grows the buffers */
         while (m > 1 && chunk_in_bytes(j, pos, pos + m) > g_chunk_bytes) m = (m + 1) / 2;
@@ -469,6 +468,18 @@ int eddsa_b200_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8
 /* ---------------------------------------------------------------------------------------------
  * device-buffer batch API (current device, asynchronous)
  * --------------------------------------------------------------------------------------------- */
+static int cur_ctx(edg_dev_t **c);
+
+/* diagnostic: read back the base-point window tables the verify kernels use on the current device */
+size_t eddsa_b200_verify_tables(uint8_t *out, size_t cap)
+{
+    edg_dev_t *c;
+    size_t bytes = edg_verify_table_bytes() - 48 * sizeof(uint32_t);   /* without the two base points at the end */
+    if (!out || cap < bytes || cur_ctx(&c)) return 0;
+    if (cudaMemcpy(out, c->wtab, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) { fail(1, "cudaMemcpy of the window tables failed"); return 0; }
+    return bytes;
+}
+
 static int cur_ctx(edg_dev_t **c)
 {
     int dev = 0, rc = engine_ready();

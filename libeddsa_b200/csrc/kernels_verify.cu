@@ -104,6 +104,7 @@ static size_t verify_chunk(int sm_count) {
 }
 
 size_t edg_verify_record_bytes(void) { return EDG_VSTATE_WORDS * sizeof(u32); }
+unsigned edg_verify_waves(void) { return EDG_VERIFY_WAVES; }
 
 // the record slab of one pass; its last 256 bytes hold the slot counters of the passes (two per pass, zeroed by the launcher)
 size_t edg_verify_scratch_bytes(int sm_count) { return verify_chunk(sm_count) * EDG_VSTATE_WORDS * sizeof(u32) + 256; }

@@ -242,6 +242,29 @@ def test_full_size_properties_2pow20(ed, cpu):
     assert (out[sample] == cpu.x25519(a[sample], pts[sample])).all()
 
 
+def test_window_tables_built_on_the_device(ed):
+    """The 2 x 32769-entry base-point tables k_wtab_build leaves in device memory: sampled entries against the
+    big-integer model, every entry against its predecessor (entry e - entry e-1 must be the table's base point:
+    checked through the affine coordinates recovered from (y+x, y-x))."""
+    import random
+    from test_host_sim import wtab_expected, WTAB_SAMPLE
+    import edmodel as em
+    tabs = ed.verify_tables()
+    rng = random.Random(9)
+    for m in range(2):
+        for e in WTAB_SAMPLE + [rng.randrange(32769) for _ in range(60)]:
+            assert tabs[m, e].tobytes() == wtab_expected(m, e), (m, e)
+    # all entries: (y+x)(y-x) = y^2 - x^2 and 2dxy consistent with the curve equation  -x^2 + y^2 = 1 + d x^2 y^2
+    P = em.P
+    inv2 = pow(2, P - 2, P)
+    for m in range(2):
+        for e in range(0, 32769, 97):
+            ypx, ymx, xy2d = (int.from_bytes(tabs[m, e, k].tobytes(), "little") for k in range(3))
+            x, y = (ypx - ymx) * inv2 % P, (ypx + ymx) * inv2 % P
+            assert (y * y - x * x - 1 - em.D * x * x * y * y) % P == 0, (m, e)
+            assert xy2d == 2 * em.D * x * y % P, (m, e)
+
+
 def test_verify_pass_boundaries(ed, cpu):
     """The two verify kernels work in passes of whole waves (303 104 signatures on 148 SMs) and hand records out in
     sorted order: batches one past a pass, with a ragged last warp, through the device API (one launch pair per

@@ -188,6 +188,29 @@ def test_ops_adversarial_verify(ops):
     assert not bad, bad[:10]
 
 
+def wtab_expected(m, e):
+    """Entry e of window table m as 96 bytes: (y+x, y-x, 2dxy) of e * 2^(128 m) * B, canonical, from the big-integer model."""
+    import edmodel as em
+    x, y = em.mul(e << (128 * m), em.B) if e else (0, 1)
+    return b"".join(v.to_bytes(32, "little") for v in ((y + x) % em.P, (y - x) % em.P, 2 * em.D * x * y % em.P))
+
+
+WTAB_SAMPLE = [0, 1, 2, 3, 7, 8, 9, 255, 256, 4095, 4096, 12345, 16384, 32767, 32768]
+
+
+def test_window_tables_host_build(ops):
+    """wtab_base / wtab_build8 (the code k_wtab_base / k_wtab_build run on the device) against the big-integer model."""
+    n = ctypes.c_uint32()
+    ops.hs_wtab.restype = ctypes.POINTER(ctypes.c_uint32)
+    tab = ops.hs_wtab(ctypes.byref(n))
+    assert n.value == 32769
+    raw = np.ctypeslib.as_array(tab, shape=(2, 32769, 24)).view(np.uint8).reshape(2, 32769, 96)
+    rng = random.Random(5)
+    for m in range(2):
+        for e in WTAB_SAMPLE + [rng.randrange(32769) for _ in range(40)]:
+            assert raw[m, e].tobytes() == wtab_expected(m, e), (m, e)
+
+
 def test_half_gcd(ops):
     """hgcd.cuh: (rho, tau) is a lattice vector (tau = rho t mod 8L), rho is odd, and both are short — for random t,
     for structured t (tiny, huge partial quotients, even-rho traps) and for the documented fallback."""
