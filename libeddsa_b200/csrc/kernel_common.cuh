@@ -37,6 +37,38 @@ __device__ __forceinline__ void msg_of(const uint8_t *&m, u64 &len, const uint8_
     else { m = msgs + (size_t)i * fixed_len; len = fixed_len; }
 }
 
+// Ragged batches (an offsets array): lanes of a warp hash messages of different lengths and the warp pays for the
+// longest.  The message kernels therefore work on tiles of consecutive operations and visit a tile in order of
+// message length: keys (length << IDX_BITS | position in tile) are sorted in shared memory (bitonic, all threads of
+// the block), so neighbouring lanes get neighbouring lengths.  Lengths are public; results go to their own slots.
+template <int N>
+__device__ __forceinline__ void block_sort_u32(u32 *key) {
+#pragma unroll 1
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll 1
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < N; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const u32 a = key[i], b = key[l];
+                    if ((a > b) == ((i & k) == 0)) { key[i] = b; key[l] = a; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// key of operation `base + e` (e < N = 2^IDX_BITS) of a ragged batch; operations past the end sort last
+template <int IDX_BITS>
+__device__ __forceinline__ u32 ragged_key(const unsigned long long *off, size_t base, int e, size_t n) {
+    if (base + e >= n) return 0xffffffffu;
+    const unsigned long long len = off[base + e + 1] - off[base + e];
+    const u32 cap = (1u << (32 - IDX_BITS)) - 2u;
+    return ((len < cap ? (u32)len : cap) << IDX_BITS) | (u32)e;
+}
+
 // Overwrite per-thread scratch that held secret-derived values (the GPU analogue of the reference's
 // burnstack(), lib/burnstack.c:12-19); volatile so the stores are not optimised away.
 __device__ __forceinline__ void scrub(fe *p, int count) {

@@ -78,17 +78,42 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_GENPUB) k_genpub(size_t n, ui
     }
 }
 
+// RAGGED = the batch has an offsets array: tiles of kThreads x EDG_BATCH consecutive signatures, visited in order of
+// message length (kernel_common.cuh: block_sort_u32); otherwise the grid-stride mapping of the other kernels.
+template <bool RAGGED>
 __global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
                                                    const unsigned long long *off, unsigned long long fixed_len) {
     extern __shared__ __align__(16) u32 s_comb[];
+    constexpr int TILE = kThreads * EDG_BATCH;
+    __shared__ u32 s_key[RAGGED ? TILE : 1];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
     const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+    // RAGGED: full rounds of one TILE per block, then the remainder split evenly over the blocks (smaller tiles), so
+    // that the last round costs every block the same; otherwise one grid-stride round per EDG_BATCH x T signatures
+    const size_t full = RAGGED ? n / ((size_t)gridDim.x * TILE) : 0;
+    const size_t rem0 = full * gridDim.x * TILE;
+    const size_t share = RAGGED ? ((n - rem0 + gridDim.x - 1) / gridDim.x + 31) / 32 * 32 : 0;     // <= TILE
+    const size_t rounds = RAGGED ? full + (n > rem0 ? 1 : 0) : 0;
+    size_t round = 0, i0 = RAGGED ? 0 : (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; RAGGED ? round < rounds : i0 < n; round++, i0 += T * EDG_BATCH) {
+        if (RAGGED) {
+            size_t lim;                                        // tile [i0, lim)
+            if (round < full) { i0 = (round * gridDim.x + blockIdx.x) * TILE; lim = i0 + TILE; }
+            else { i0 = rem0 + blockIdx.x * share; lim = i0 + share < n ? i0 + share : n; }
+            __syncthreads();                                   // the previous tile's keys are no longer needed
+            for (int e = threadIdx.x; e < TILE; e += blockDim.x) s_key[e] = i0 < lim ? ragged_key<10>(off, i0, e, lim) : 0xffffffffu;
+            block_sort_u32<TILE>(s_key);
+        }
+        auto op_index = [&](int k) -> size_t {
+            if (!RAGGED) return i0 + (size_t)k * T;
+            const u32 key = s_key[threadIdx.x + kThreads * k];
+            return key == 0xffffffffu ? n : i0 + (key & (TILE - 1));
+        };
         fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH], AR[2 * EDG_BATCH];     // AR: secret scalar a and nonce r of each signature
         int cnt = 0;
 #pragma unroll 1
         for (int k = 0; k < EDG_BATCH; k++) {
-            const size_t i = i0 + (size_t)k * T;
+            const size_t i = op_index(k);
             if (i >= n) break;
             const uint8_t *m; u64 len;
             msg_of(m, len, msgs, off, fixed_len, i);
@@ -97,10 +122,11 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_
             fe_copy(X[k], R.X); fe_copy(Y[k], R.Y); fe_copy(Z[k], R.Z);
             cnt++;
         }
+        if (RAGGED && cnt == 0) continue;                      // (public: no work for this thread in the last round)
         fe_batch_inv(Z, cnt);
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
-            const size_t i = i0 + (size_t)k * T;
+            const size_t i = op_index(k);
             u32 p[8], o[16];
             const uint8_t *m; u64 len;
             msg_of(m, len, msgs, off, fixed_len, i);
@@ -132,7 +158,8 @@ int edg_fixedbase_init(void) {
     cudaError_t e;
     e = cudaFuncSetAttribute(k_x25519_base, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
     e = cudaFuncSetAttribute(k_genpub, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
-    e = cudaFuncSetAttribute(k_sign, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_sign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_sign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
     return 0;
 }
 
@@ -153,8 +180,15 @@ int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, int sm_count, 
 int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
                     const unsigned long long *off, unsigned long long fixed_len, int sm_count, void *stream) {
     if (n == 0) return 0;
-    int g = grid_for(k_sign, n, kCombBytes, sm_count, nullptr);
-    k_sign<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
+    if (off) {                                                 // ragged: tiles of kThreads x EDG_BATCH signatures per block
+        int bps = 0;
+        grid_for(k_sign<true>, n, kCombBytes, sm_count, &bps);
+        const size_t tiles = (n + (size_t)kThreads * EDG_BATCH - 1) / ((size_t)kThreads * EDG_BATCH), cap = (size_t)sm_count * bps;
+        k_sign<true><<<(unsigned)(tiles < cap ? tiles : cap), kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
+    } else {
+        int g = grid_for(k_sign<false>, n, kCombBytes, sm_count, nullptr);
+        k_sign<false><<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
+    }
     return (int)cudaGetLastError();
 }
 

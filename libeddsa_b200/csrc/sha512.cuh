@@ -52,6 +52,15 @@ EDG_HD u32 bswap32(u32 x) {
 #endif
 }
 
+// low 32 bits of (hi:lo) >> sh, 0 <= sh < 32
+EDG_HD u32 funnel_r(u32 lo, u32 hi, u32 sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+
 // big-endian 64-bit word from two little-endian 32-bit words holding bytes [0..3], [4..7]
 EDG_HD u64 be64_from_le_words(u32 w0, u32 w1) { return ((u64)bswap32(w0) << 32) | bswap32(w1); }
 
@@ -94,6 +103,16 @@ EDG_HD u64 sha512_msg_word(const uint8_t *msg, u64 len, u64 m) {
         if ((((uintptr_t)p) & 7) == 0) {
             const u32 *q = (const u32 *)p;
             return be64_from_le_words(q[0], q[1]);
+        }
+        if (m + 12 <= len) {
+            // unaligned, at least 4 more message bytes behind the word: three aligned 32-bit loads and two funnel
+            // shifts.  The loads stay inside [message start rounded down to 4, message end) — allocations start
+            // 4-byte aligned, so nothing outside the caller's buffer is touched.
+            const uintptr_t ad = (uintptr_t)p;
+            const u32 *q = (const u32 *)(ad & ~(uintptr_t)3);
+            const u32 sh = (u32)(ad & 3) * 8;
+            const u32 w0 = q[0], w1 = q[1], w2 = q[2];
+            return be64_from_le_words(funnel_r(w0, w1, sh), funnel_r(w1, w2, sh));
         }
         u64 v = 0;
 #pragma unroll
@@ -142,6 +161,28 @@ EDG_HD void sha512_prefixed(u64 state[8], const u64 *pre, const uint8_t *msg, u6
                 const u32 *q = (const u32 *)p;
                 for (int k = 0; k < 16; k++) w[k] = be64_from_le_words(q[2 * k], q[2 * k + 1]);
 #endif
+            } else if (m0 + 144 <= len) {
+                // unaligned full block with 16 more message bytes behind it: nine aligned 128-bit loads (the block's
+                // bytes start 0..15 bytes into them) and funnel shifts; word offset and byte shift are per message
+                const uintptr_t ad = (uintptr_t)p;
+                const u32 ws = (u32)(ad >> 2) & 3u, sh = (u32)(ad & 3) * 8;
+                u32 x[36];
+#if defined(__CUDA_ARCH__)
+                const uint4 *q = (const uint4 *)(ad & ~(uintptr_t)15);
+#pragma unroll
+                for (int k = 0; k < 9; k++) { const uint4 v = __ldg(q + k); x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w; }
+#else
+                const u32 *q = (const u32 *)(ad & ~(uintptr_t)15);
+                for (int k = 0; k < 36; k++) x[k] = q[k];
+#endif
+                // y[k] = x[k + ws] for k = 0..32 (two conditional moves per word: shift by 2, then by 1)
+#pragma unroll
+                for (int k = 0; k < 34; k++) x[k] = (ws & 2u) ? x[k + 2] : x[k];
+#pragma unroll
+                for (int k = 0; k < 33; k++) x[k] = (ws & 1u) ? x[k + 1] : x[k];
+#pragma unroll
+                for (int k = 0; k < 16; k++)
+                    w[k] = be64_from_le_words(funnel_r(x[2 * k], x[2 * k + 1], sh), funnel_r(x[2 * k + 1], x[2 * k + 2], sh));
             } else {
 #pragma unroll
                 for (int k = 0; k < 16; k++) w[k] = sha512_msg_word(msg, len, m0 + 8 * k);

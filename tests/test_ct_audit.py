@@ -23,7 +23,7 @@ def libpath():
 
 def test_secret_kernels_are_constant_time(libpath):
     results = ct_audit.run(libpath)
-    assert {r["kernel"] for r in results} == {"k_x25519", "k_x25519_base", "k_genpub", "k_sign", "k_sk_convert"}
+    assert {r["kernel"] for r in results} == {"k_x25519", "k_x25519_base", "k_genpub", "k_signILb0", "k_signILb1", "k_sk_convert"}
     for r in results:
         assert "error" not in r, r
         assert r["secret_loads"] > 0, f"{r['kernel']}: the audit saw no secret loads (taint source not found)"

@@ -176,6 +176,25 @@ def test_ragged_and_unaligned_messages(ed, cpu):
     assert ed.ed25519_verify_batch(sig, pub, blob, off=off).all()
 
 
+def test_ragged_batch_across_sign_tiles(ed, cpu):
+    """Ragged batches are signed in tiles of 1024 signatures visited in order of message length (full rounds of one
+    tile per block, then an evenly split remainder): a batch larger than one round, lengths 0..400, every signature
+    verified, a sample and both ends of the batch compared with the oracle."""
+    rng = np.random.default_rng(350)
+    n = 148 * 2 * 1024 + 5000 + 13
+    lens = rng.integers(0, 401, n)
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    blob = rng.integers(0, 256, int(off[-1]) + 16, dtype=np.uint8)
+    sec = rand_bytes(rng, n, 32)
+    pub = ed.ed25519_genpub_batch(sec)
+    sig = ed.ed25519_sign_batch(sec, pub, blob, off=off)
+    assert ed.ed25519_verify_batch(sig, pub, blob, off=off).all()
+    sample = np.concatenate([np.arange(0, 600), np.arange(n - 600, n), rng.integers(0, n, 1200)])
+    sub = [blob[int(off[i]):int(off[i + 1])].tobytes() for i in sample]
+    sblob, soff = gu.ragged(sub)
+    assert (sig[sample] == cpu.sign(sec[sample], pub[sample], sblob, off=soff)).all()
+
+
 def test_random_differential_medium(ed, cpu):
     """2^14 fresh operations of every kind vs the CPU checker, with 1/8 of the signatures corrupted."""
     rng = np.random.default_rng(400)

@@ -13,7 +13,9 @@ res = {}
 for name, lens in (("fixed64_as_offsets", torch.full((n,), 64, dtype=torch.int64, device=dev)),
                    ("ragged_0_128", torch.randint(0, 129, (n,), device=dev, generator=g)),
                    ("ragged_0_128_mult16", torch.randint(0, 9, (n,), device=dev, generator=g) * 16),
-                   ("ragged_0_1024", torch.randint(0, 1025, (n,), device=dev, generator=g))):
+                   ("ragged_0_1024", torch.randint(0, 1025, (n,), device=dev, generator=g)),
+                   ("ragged_0_1024_sorted_by_length", torch.sort(torch.randint(0, 1025, (n,), device=dev, generator=g))[0]),
+                   ("ragged_0_1024_mult16_sorted", torch.sort(torch.randint(0, 65, (n,), device=dev, generator=g) * 16)[0])):
     off = torch.zeros(n + 1, dtype=torch.int64, device=dev); off[1:] = torch.cumsum(lens, 0)
     total = int(off[-1].item())
     blob = torch.randint(0, 256, (total + 16,), dtype=torch.uint8, device=dev, generator=g)

@@ -2,7 +2,7 @@
 """Constant-time SASS audit of the secret-key kernels (sm_100a).
 
 Static taint analysis over the disassembly (cuobjdump -sass) of each kernel that touches a secret
-(k_x25519, k_x25519_base, k_genpub, k_sign, k_sk_convert):
+(k_x25519, k_x25519_base, k_genpub, k_sign<false>, k_sign<true>, k_sk_convert):
 
   * sources : every value loaded from global memory through a pointer derived from a SECRET kernel
               parameter (the secret key / scalar arrays); everything computed from such values;
@@ -41,7 +41,8 @@ SECRET_PARAMS = {
     "k_x25519E": {"params": ["n", "out", "scalar", "point"], "secret": ["scalar"]},
     "k_x25519_base": {"params": ["n", "out", "scalar"], "secret": ["scalar"]},
     "k_genpub": {"params": ["n", "pub", "sec"], "secret": ["sec"]},
-    "k_sign": {"params": ["n", "sig", "sec", "pub", "msgs", "off", "fixed_len"], "secret": ["sec"]},
+    "k_signILb0": {"params": ["n", "sig", "sec", "pub", "msgs", "off", "fixed_len"], "secret": ["sec"]},   # fixed-length batches
+    "k_signILb1": {"params": ["n", "sig", "sec", "pub", "msgs", "off", "fixed_len"], "secret": ["sec"]},   # ragged batches (length-sorted tiles)
     "k_sk_convert": {"params": ["n", "out", "in"], "secret": ["in"]},
 }
 PUBLIC_KERNELS = ["k_verify", "k_pk_convert"]
