@@ -9,12 +9,14 @@
 //     fe_canon / fe_to_words produce the unique value in [0, p).
 //   * a multiplication is 64 IMAD.WIDE.U32 products accumulated by hardware carry chains
 //     (IMAD.WIDE.U32 Rd, Pc, a, b, Rd  /  IMAD.WIDE.U32.X ... with carry-in), organised as 16 rows of
-//     four products in an even-word and an odd-word accumulator, one 15-word merge add, and 8 more
-//     wide products that fold the high half back with 2^256 = 38 (mod p): 72 wide multiplies per
-//     multiplication, 44 per squaring (28 doubled cross products + 8 diagonal + 8 fold).
-//     Measured on B200 (tools/fe32_proto.cu, profiles/r01_pipe_microbench.md): 1.11e11 mul/s,
-//     1.54e11 sq/s per GPU = 86 % / 73 % of the IMAD.WIDE issue peak — 1.57x / 1.20x the 10 x 25.5-bit
-//     limb form this engine started with (100 / 55 wide multiplies, no carry chains).
+//     four products in an even-word and an odd-word accumulator; the high half is folded back with
+//     2^256 = 38 (mod p) by 8 more wide products riding carry chains on the register pairs the accumulators
+//     already live in (before the even/odd merge), then the halves are merged: 72 wide multiplies per
+//     multiplication, 44 per squaring (28 doubled cross products + 8 diagonal + 8 fold).  A row's carry-out
+//     word is only caught where its top 64-bit slot can overflow (7 of 16 rows; 5 of 13 in a squaring).
+//     Measured on B200 (tools/fe32_proto.cu, tools/fe_kara.cu, profiles/r01_pipe_microbench.md): 1.13e11
+//     mul/s per GPU = 87 % of the IMAD.WIDE issue peak in a dependent chain, 96 % in a point-operation mix —
+//     1.6x the 10 x 25.5-bit limb form this engine started with (100 / 55 wide multiplies, no carry chains).
 //   * IMAD.WIDE has half the issue rate of IMAD on this part (32 vs 64 thread-instr/clk/SM, measured),
 //     so the design minimises the NUMBER of wide multiplies; additions run on the otherwise idle
 //     ALU pipe as IADD3.X carry chains.
