@@ -27,7 +27,7 @@ namespace {
 constexpr int kVThreads = EDG_VTHREADS;
 
 // stage 1: one signature per thread -> one EDG_VSTATE_WORDS-word record.  Records are handed out sorted by window
-// count: signatures needing at most EDG_NWIN_SPLIT windows (95 %) fill the record array from the front, the others
+// count: signatures needing more than EDG_NWIN_SPLIT windows (5 %) fill the record array from the front, the others
 // from the back, so a warp of the loop kernel (which runs the maximum over its lanes) almost never waits for a
 // single long lane: 33.9 -> 33.05 windows on average.  Slots come from two counters (one warp-aggregated atomic each).
 #define EDG_NWIN_SPLIT 33
@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t
     base_hi = __shfl_sync(0xffffffffu, base_hi, 0);
     if (!live) return;
     const unsigned below = (1u << lane) - 1u;
-    const size_t slot = nwin <= EDG_NWIN_SPLIT ? (size_t)base_lo + __popc(lo & below) : n - 1 - ((size_t)base_hi + __popc(hi & below));
+    // the few long ones go to the FRONT of the array (their warps start first, the kernel's tail is made of short ones)
+    const size_t slot = nwin <= EDG_NWIN_SPLIT ? n - 1 - ((size_t)base_lo + __popc(lo & below)) : (size_t)base_hi + __popc(hi & below);
     ed25519_verify_front_points(state + slot * EDG_VSTATE_WORDS, v, nwin, (u32)k, sg, pk);
 }
 
