@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kVThreads, EDG_LB_VLOOP) k_verify(size_t n, ui
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ((k & ~(size_t)31) >= n) return;
     const u32 *rec = state + (k < n ? k : n - 1) * EDG_VSTATE_WORDS;
-    const u32 r = ed25519_verify_loop(rec, wtab);
+    __shared__ uint4 s_stage[16 * kVThreads];                  // 2 table entries x 8 x 16 bytes per thread, chunk-major
+    const u32 r = ed25519_verify_loop(rec, wtab, reinterpret_cast<u32 *>(s_stage));
     if (k < n) ok[rec[602]] = (uint8_t)r;
 }
 

@@ -464,7 +464,11 @@ EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, con
     ed25519_verify_front_points(state, v, nwin, 0, sig, pub);
 }
 
-EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab) {
+// stage (device only, may be null): this block's shared-memory staging area, 16 chunks x blockDim.x threads x 16 bytes.
+// At the start of a window every thread starts asynchronous copies (cp.async, no registers involved) of the two
+// table entries the window will add; they arrive while the four doublings run, so the additions find them in
+// shared memory instead of waiting ~1 us for the record in L2 / HBM (4.4 % of the loop's stall samples).
+EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab, u32 *stage = 0) {
     u32 et[8], er[8], es[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) { et[i] = state[576 + i]; er[i] = state[584 + i]; es[i] = state[592 + i]; }
@@ -491,6 +495,19 @@ EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab) {
     for (int j = nwin - 1; j >= 0; j--) {
         const bool has_b = ((j & 3) == 0) && j < 32;
         const int last = has_b ? 8 : 6;
+#if defined(__CUDA_ARCH__)
+        if (stage) {
+            const int d0 = sc_digit16(et, j), d1 = sc_digit16(er, j);
+            const u32 *s0 = qtab + 32 * (d0 < 0 ? -d0 : d0), *s1 = qtab + 288 + 32 * (d1 < 0 ? -d1 : d1);
+            const u32 dst = (u32)__cvta_generic_to_shared(stage) + 16u * threadIdx.x;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * blockDim.x * c), "l"(s0 + 4 * c) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + 16u * blockDim.x * (8 + c)), "l"(s1 + 4 * c) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+#endif
 #pragma unroll 1
         for (int step = (j == nwin - 1 ? 4 : 0); step < last; step++) {
             fe e, f, g, h;
@@ -513,6 +530,17 @@ EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab) {
                     const u32 neg = (u32)(dg >> 31);
                     const u32 absd = ((u32)dg ^ neg) - neg;
                     ge_cached q;
+#if defined(__CUDA_ARCH__)
+                    if (stage) {
+                        if (step == 4) asm volatile("cp.async.wait_group 0;" ::: "memory");     // this thread's own copies only
+                        const uint4 *sp = reinterpret_cast<const uint4 *>(stage) + threadIdx.x + (step == 4 ? 0 : 8) * blockDim.x;
+                        u32 w[32];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) { const uint4 v = sp[c * blockDim.x]; w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w; }
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { q.ypx.v[i] = w[i]; q.ymx.v[i] = w[8 + i]; q.z2.v[i] = w[16 + i]; q.t2d.v[i] = w[24 + i]; }
+                    } else
+#endif
                     ge_cached_load(q, qtab + (step == 4 ? 0 : 288) + 32 * absd);
                     ge_cached_cneg(q, neg);
                     fe_copy(ypx, q.ypx); fe_copy(ymx, q.ymx); fe_copy(t2d, q.t2d);
