@@ -342,6 +342,7 @@ def run_ours(args):
             "wide_multiplies_per_op_executed": products(OURS_FM["verify"]),
             "wide_multiplies_per_op_reference_fm": products(REF_FM["verify"]),
             "kernel_ms_per_launch": kernel_ms,
+            "stages": ncu_stages(),
             "traffic": ncu_traffic(n),
             "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of both stages from the ncu --set full capture on 2^18 signatures "
                             "(profiles/r01_ncu_summary.json), scaled to this batch; ~7 KB/signature = the 2.4 KB record the front stage "
@@ -383,6 +384,18 @@ def ncu_traffic(n):
         d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
         per_op = sum(d[k]["dram_read_bytes"] + d[k]["dram_write_bytes"] for k in ("verify_loop", "verify_front")) / d["ops_per_launch"]
         return int(per_op * n)
+    except Exception:
+        return None
+
+
+def ncu_stages():
+    """The two kernels of a verify pass as captured by ncu on 2^18 signatures (profiles/r01_ncu_summary.json): share of the
+    pass and multiplier-pipe utilisation of each — context for the pass-level roofline above, not measured live."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
+        tot = d["verify_front"]["duration_ms"] + d["verify_loop"]["duration_ms"]
+        return {d[k]["kernel"]: {"share_of_pass": round(d[k]["duration_ms"] / tot, 3), "fmaheavy_pipe_busy_pct": d[k]["fmaheavy_pipe_busy_pct"],
+                                 "registers": d[k]["registers_per_thread"]} for k in ("verify_front", "verify_loop")}
     except Exception:
         return None
 
