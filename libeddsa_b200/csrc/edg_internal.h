@@ -23,6 +23,7 @@ int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *p
 /* window table of the base point used by verify: built once per device, read-only afterwards */
 size_t edg_verify_table_bytes(void);
 int edg_verify_table_init(void *table, void *stream);
+void edg_verify_debug_full_scalars(int on);      /* test hook: force the full-length (rho, tau) = (1, t) path */
 unsigned edg_verify_launches(size_t n, int sm_count); /* kernels one edg_launch_verify(n) launches */
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
                       const unsigned long long *off, unsigned long long fixed_len, void *scratch, const void *table,

@@ -103,7 +103,7 @@ EDG_HD u32 hg_less8(const u32 x[8], const u32 y[8]) {
 //     at once (signs fixed up afterwards if the approximation went one step too far);
 //   * single step with an under-estimated quotient when the leading words allow no Lehmer step (large partial
 //     quotient, or the last step across 2^128).
-EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8]) {
+EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8], bool force_fallback = false) {
     const u32 N8L[8] = EDG_SC_8L_INIT;
     u32 ru[8], rv[8], bu[6], bv[6];
 #pragma unroll
@@ -111,11 +111,11 @@ EDG_HD void half_gcd(u32 rho_abs[8], u32 &rho_neg, u32 tau[8], const u32 t[8]) {
 #pragma unroll
     for (int i = 0; i < 6; i++) { bu[i] = 0; bv[i] = 0; }
     bv[0] = 1;
-    bool fallback = false;
+    bool fallback = force_fallback;                        // (test hook: exercise the full-length path on any input)
     // Every pass strictly decreases max(ru, rv) (a Lehmer pass by at least one bit), so ~130 passes suffice; the
     // cap is a belt-and-braces bound so that no input can ever keep a GPU thread spinning.
 #pragma unroll 1
-    for (int pass = 0;; pass++) {
+    for (int pass = 0; !fallback; pass++) {
         if (pass >= 1024) { fallback = true; break; }
         const bool big = (rv[4] | rv[5] | rv[6] | rv[7]) != 0;      // rv >= 2^128: keep reducing
         if (!big) {

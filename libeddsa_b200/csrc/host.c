@@ -119,6 +119,7 @@ static void global_init(void)
     if (g_nlist == 0) g_list[g_nlist++] = 0;
     g_nactive = g_nlist;
     if (chunk && atoi(chunk) > 0) g_chunk_bytes = (size_t)atoi(chunk) << 20;
+    if (getenv("EDDSA_B200_DEBUG_FULL_SCALARS") && atoi(getenv("EDDSA_B200_DEBUG_FULL_SCALARS")) > 0) edg_verify_debug_full_scalars(1);
 }
 
 static int engine_ready(void)

@@ -33,7 +33,7 @@ constexpr int kVThreads = EDG_VTHREADS;
 #define EDG_NWIN_SPLIT 33
 __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t n, size_t first, const uint8_t *sig, const uint8_t *pub,
                                                      const uint8_t *msgs, const unsigned long long *off, unsigned long long fixed_len,
-                                                     u32 *state, unsigned int *counters) {
+                                                     u32 *state, unsigned int *counters, int full_scalars) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if ((k & ~(size_t)31) >= n) return;                    // whole warps stay (full-mask votes below)
     const bool live = k < n;
@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t
     msg_of(m, len, msgs, off, fixed_len, i);
     const u32 *sg = reinterpret_cast<const u32 *>(sig + 64 * i), *pk = reinterpret_cast<const u32 *>(pub + 32 * i);
     verify_scalars v;
-    const int nwin = ed25519_verify_front_scalars(v, sg, pk, m, len);
+    const int nwin = ed25519_verify_front_scalars(v, sg, pk, m, len, full_scalars != 0);
     __syncwarp();
     const unsigned lane = threadIdx.x & 31u;
     const unsigned lo = __ballot_sync(0xffffffffu, live && nwin <= EDG_NWIN_SPLIT);
@@ -123,6 +123,10 @@ int edg_verify_table_init(void *table, void *stream) {
     return (int)cudaGetLastError();
 }
 
+// test hook (EDDSA_B200_DEBUG_FULL_SCALARS=1): every signature takes the full-length fallback (rho, tau) = (1, t)
+static int g_full_scalars = 0;
+void edg_verify_debug_full_scalars(int on) { g_full_scalars = on; }
+
 // kernels edg_launch_verify(n, ..) launches: two per pass
 unsigned edg_verify_launches(size_t n, int sm_count) {
     const size_t chunk = verify_chunk(sm_count);
@@ -137,7 +141,7 @@ int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *
     for (size_t first = 0; first < n; first += chunk) {
         const size_t m = n - first < chunk ? n - first : chunk;
         cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream);
-        k_verify_front<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch, counters);
+        k_verify_front<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch, counters, g_full_scalars);
         k_verify<<<(unsigned)((m + kVThreads - 1) / kVThreads), kVThreads, 0, (cudaStream_t)stream>>>(m, ok + first, (const u32 *)scratch, (const u32 *)table);
     }
     return (int)cudaGetLastError();

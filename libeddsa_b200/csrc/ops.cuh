@@ -413,7 +413,7 @@ EDG_HD int sc_digit16(const u32 *e, int j) { return (int)((e[j >> 3] >> (4 * (j 
 // agree on their trip count) and calls part 2.
 struct verify_scalars { u32 et[8], er[8], es[8], rho_neg; };
 
-EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
+EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, bool full_scalars = false) {
     // t = H(R || A || M) mod L, bytes exactly as given (Q4)                                    :166-171
     u64 pre[8], st[8];
     u32 h[16], t[8], s[8];
@@ -427,7 +427,7 @@ EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const
     sha512_prefixed<8>(st, pre, msg, len);
     sha512_state_to_le_words(h, st);
     sc_reduce512(t, h);
-    half_gcd(v.er, v.rho_neg, v.et, t);                   // er = |rho|, et = tau
+    half_gcd(v.er, v.rho_neg, v.et, t, full_scalars);     // er = |rho|, et = tau  (full_scalars: (1, t), the fallback)
     load_words8(h, sig + 8);
     sc_reduce256(s, h);                                   // no range check on S (Q1)               :163
 #pragma unroll
@@ -458,9 +458,9 @@ EDG_HD void ed25519_verify_front_points(u32 *state, const verify_scalars &v, int
     state[602] = index;
 }
 
-EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len) {
+EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, bool full_scalars = false) {
     verify_scalars v;
-    const int nwin = ed25519_verify_front_scalars(v, sig, pub, msg, len);
+    const int nwin = ed25519_verify_front_scalars(v, sig, pub, msg, len, full_scalars);
     ed25519_verify_front_points(state, v, nwin, 0, sig, pub);
 }
 
@@ -574,8 +574,8 @@ EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab, u32 *stage = 0
     return is_o & (good & 1u);
 }
 
-EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *state, const u32 *wtab) {
-    ed25519_verify_front(state, sig, pub, msg, len);
+EDG_HD u32 ed25519_verify_op(const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, u32 *state, const u32 *wtab, bool full_scalars = false) {
+    ed25519_verify_front(state, sig, pub, msg, len, full_scalars);
     return ed25519_verify_loop(state, wtab);
 }
 

@@ -47,6 +47,10 @@ void hs_batch_inv(uint8_t *z, int cnt) {   // z: cnt x 32 bytes, in place
     fe_batch_inv(t, cnt);
     for (int k = 0; k < cnt; k++) { u32 w[8]; fe_to_words(w, t[k]); memcpy(z + 32 * k, w, 32); }
 }
+int hs_verify_full(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64_t len) {   // the (1, t) fallback path
+    u32 s[16], p[8], qtab[EDG_VSTATE_WORDS]; memcpy(s, sig, 64); memcpy(p, pub, 32);
+    return (int)ed25519_verify_op(s, p, msg, len, qtab, host_wtab(), true);
+}
 int hs_last_nwin(void) { return edg_last_nwin; }
 void hs_half_gcd(uint32_t *rho_abs, uint32_t *rho_neg, uint32_t *tau, const uint32_t *t) { u32 n; half_gcd(rho_abs, n, tau, t); *rho_neg = n; }
 void hs_counts(unsigned long *mul, unsigned long *sq, int reset) { *mul = edg_cnt_mul; *sq = edg_cnt_sq; if (reset) edg_cnt_mul = edg_cnt_sq = 0; }

@@ -284,6 +284,37 @@ def test_window_tables_built_on_the_device(ed):
             assert xy2d == 2 * em.D * x * y % P, (m, e)
 
 
+def test_verify_full_length_fallback_path_on_the_device(cpu):
+    """The (rho, tau) = (1, t) fallback of the half-size-scalar verification (64 windows instead of ~33) can only be
+    reached by challenge values nobody can construct, so a debug switch (EDDSA_B200_DEBUG_FULL_SCALARS=1, read once
+    at library start-up) forces it for every signature: the adversarial fixtures and a corrupted random batch must be
+    decided exactly as before.  Runs in a fresh interpreter because the switch is read at initialisation."""
+    import subprocess, sys, os, textwrap
+    code = textwrap.dedent("""
+        import os, sys, numpy as np
+        sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+        import libeddsa_b200 as ed, golden_util as gu
+        from cpu_ref import best_cpu_impl
+        cpu = best_cpu_impl()
+        sig, pub, msgs, cls, expect = gu.verify_adv()
+        blob, off = gu.ragged(msgs)
+        got = ed.ed25519_verify_batch(sig, pub, blob, off=off)
+        assert (got == expect).all(), np.nonzero(got != expect)[0][:10]
+        rng = np.random.default_rng(77); n = 40000
+        sec = rng.integers(0, 256, (n, 32), dtype=np.uint8); m = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+        pk = ed.ed25519_genpub_batch(sec); sg = ed.ed25519_sign_batch(sec, pk, m, fixed_len=64)
+        sg[::7, rng.integers(0, 64)] ^= 0x04
+        ok = ed.ed25519_verify_batch(sg, pk, m, fixed_len=64)
+        assert (ok == cpu.verify(sg, pk, m, fixed_len=64)).all()
+        assert 0.8 * n < ok.sum() < n
+        print("full-scalar path ok", int(ok.sum()))
+    """)
+    env = dict(os.environ, EDDSA_B200_DEBUG_FULL_SCALARS="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "full-scalar path ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_verify_pass_boundaries(ed, cpu):
     """The two verify kernels work in passes of whole waves (303 104 signatures on 148 SMs) and hand records out in
     sorted order: batches one past a pass, with a ragged last warp, through the device API (one launch pair per

@@ -186,6 +186,11 @@ def test_ops_adversarial_verify(ops):
         if got != expect[i]:
             bad.append((i, int(cls[i])))
     assert not bad, bad[:10]
+    # the full-length fallback (rho, tau) = (1, t): 64 windows, every signature — it must decide identically
+    for i in list(range(0, len(sig), 11)) + [i for i in range(len(sig)) if cls[i] >= 16][::3]:
+        got = ops.hs_verify_full(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
+        assert got == expect[i], (i, int(cls[i]))
+        assert 56 <= ops.hs_last_nwin() <= 64
 
 
 def wtab_expected(m, e):
