@@ -74,6 +74,42 @@ __device__ __forceinline__ void fe_mul_k(fe &r, const fe &a, const fe &b) {
 #endif
 }
 
+// squaring variant: the eight diagonal squares as independent products added by one 16-word carry chain (instead of
+// an 8-link IMAD.WIDE.X chain after the doubling shift)
+__device__ __forceinline__ void fe_sq_v(fe &r, const fe &a) {
+#if defined(__CUDA_ARCH__)
+    u32 w[17], od[17];
+#pragma unroll
+    for (int i = 0; i < 17; i++) w[i] = od[i] = 0;
+#define EDG_SQ_OD(i, M) M<(8 - (i)) / 2>(od + 2 * (i), a.v + (i) + 1, a.v[i]);
+#define EDG_SQ_EV(i, M) M<(7 - (i)) / 2>(w + 2 * (i) + 2, a.v + (i) + 2, a.v[i]);
+    EDG_SQ_OD(0, cmadf) EDG_SQ_EV(0, cmadf)
+    EDG_SQ_OD(1, cmad)  EDG_SQ_EV(1, cmadf)
+    EDG_SQ_OD(2, cmadf) EDG_SQ_EV(2, cmad)
+    EDG_SQ_OD(3, cmad)  EDG_SQ_EV(3, cmadf)
+    EDG_SQ_OD(4, cmadf) EDG_SQ_EV(4, cmad)
+    EDG_SQ_OD(5, cmad)  EDG_SQ_EV(5, cmadf)
+    EDG_SQ_OD(6, cmadf)
+#undef EDG_SQ_OD
+#undef EDG_SQ_EV
+    u32 d[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const u64 q = mulw(a.v[i], a.v[i]); d[2 * i] = (u32)q; d[2 * i + 1] = (u32)(q >> 32); }
+    merge_odd(w, od);
+#pragma unroll
+    for (int k = 15; k > 0; k--) w[k] = (w[k] << 1) | (w[k - 1] >> 31);
+    w[0] = 0;
+    asm("add.cc.u32 %0, %0, %16; addc.cc.u32 %1, %1, %17; addc.cc.u32 %2, %2, %18; addc.cc.u32 %3, %3, %19; addc.cc.u32 %4, %4, %20; addc.cc.u32 %5, %5, %21; "
+        "addc.cc.u32 %6, %6, %22; addc.cc.u32 %7, %7, %23; addc.cc.u32 %8, %8, %24; addc.cc.u32 %9, %9, %25; addc.cc.u32 %10, %10, %26; addc.cc.u32 %11, %11, %27; "
+        "addc.cc.u32 %12, %12, %28; addc.cc.u32 %13, %13, %29; addc.cc.u32 %14, %14, %30; addc.u32 %15, %15, %31;"
+        : "+r"(w[0]), "+r"(w[1]), "+r"(w[2]), "+r"(w[3]), "+r"(w[4]), "+r"(w[5]), "+r"(w[6]), "+r"(w[7]), "+r"(w[8]), "+r"(w[9]), "+r"(w[10]), "+r"(w[11]),
+          "+r"(w[12]), "+r"(w[13]), "+r"(w[14]), "+r"(w[15])
+        : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(d[8]), "r"(d[9]), "r"(d[10]), "r"(d[11]),
+          "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15]));
+    fe_fold_sq(r, w);
+#endif
+}
+
 template <int MODE> __global__ void __launch_bounds__(128, 4) k_chain(u32 *out, int iters) {
     fe a, b, c, d;
     for (int i = 0; i < 8; i++) { a.v[i] = threadIdx.x * 2654435761u + i * 40503u + blockIdx.x; b.v[i] = a.v[i] * 3u + 7u; c.v[i] = a.v[i] ^ 0x5555u; d.v[i] = b.v[i] + 99u; }
@@ -81,6 +117,10 @@ template <int MODE> __global__ void __launch_bounds__(128, 4) k_chain(u32 *out, 
     for (int it = 0; it < iters; it++) {
         if (MODE == 0) { fe_mul(a, a, b); fe_mul(b, b, a); }
         else if (MODE == 1) { fe_mul_k(a, a, b); fe_mul_k(b, b, a); }
+        else if (MODE == 4) { fe_sq(a, a); fe_sq(b, b); }
+        else if (MODE == 5) { fe_sq_v(a, a); fe_sq_v(b, b); }
+        else if (MODE == 6) { fe_sq(a, a); }
+        else if (MODE == 7) { fe_sq_v(a, a); }
         else if (MODE == 2) {      // doubling + addition tail mix, plain
             fe e, f, g, h; fe_sq(e, a); fe_sq(f, b); fe_sq(g, c); fe_add(h, a, b); fe_sq(h, h); fe_add(e, e, f); fe_sub(f, e, h); fe_sub(g, g, f);
             fe_mul(a, e, f); fe_mul(b, g, h); fe_mul(c, f, g); fe_mul(d, e, h);
@@ -104,6 +144,9 @@ __global__ void k_check(u32 *bad, const u32 *in, int n) {
     fe_mul(r0, a, b); fe_mul_k(r1, a, b);
     fe_canon(r0, r0); fe_canon(r1, r1);
     u32 d = 0; for (int k = 0; k < 8; k++) d |= r0.v[k] ^ r1.v[k];
+    fe_sq(r0, a); fe_sq_v(r1, a);
+    fe_canon(r0, r0); fe_canon(r1, r1);
+    for (int k = 0; k < 8; k++) d |= r0.v[k] ^ r1.v[k];
     if (d) atomicAdd(bad, 1u);
 }
 
@@ -122,13 +165,15 @@ int main() {
     cudaDeviceProp p; CK(cudaGetDeviceProperties(&p, 0)); const int nsm = p.multiProcessorCount, iters = 1000;
     u32 *out; CK(cudaMalloc(&out, (size_t)nsm * 4 * 128 * 4));
     cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    const char *names[4] = {"mul_chain", "mul_chain_karatsuba", "point_mix", "point_mix_karatsuba"};
-    for (int mode = 0; mode < 4; mode++) {
+    const char *names[8] = {"mul_chain", "mul_chain_karatsuba", "point_mix", "point_mix_karatsuba", "sq_chain_x2", "sq_chain_x2_variant", "sq_chain_x1", "sq_chain_x1_variant"};
+    for (int mode = 0; mode < 8; mode++) {
         float best = 1e30f;
         for (int rep = 0; rep < 4; rep++) {
             CK(cudaEventRecord(e0));
             if (mode == 0) k_chain<0><<<nsm * 4, 128>>>(out, iters); else if (mode == 1) k_chain<1><<<nsm * 4, 128>>>(out, iters);
-            else if (mode == 2) k_chain<2><<<nsm * 4, 128>>>(out, iters); else k_chain<3><<<nsm * 4, 128>>>(out, iters);
+            else if (mode == 2) k_chain<2><<<nsm * 4, 128>>>(out, iters); else if (mode == 3) k_chain<3><<<nsm * 4, 128>>>(out, iters);
+            else if (mode == 4) k_chain<4><<<nsm * 4, 128>>>(out, iters); else if (mode == 5) k_chain<5><<<nsm * 4, 128>>>(out, iters);
+            else if (mode == 6) k_chain<6><<<nsm * 4, 128>>>(out, iters); else k_chain<7><<<nsm * 4, 128>>>(out, iters);
             CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); if (rep && ms < best) best = ms;
         }
         printf(" \"%s_ms\": %.4f,\n", names[mode], best);
