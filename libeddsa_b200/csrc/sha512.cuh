@@ -42,7 +42,18 @@ static const u64 h_K512[80] = {
     0x28db77f523047d84ULL, 0x32caab7b40c72493ULL, 0x3c9ebe0a15c9bebcULL, 0x431d67c49c100d4cULL,
     0x4cc5d4becb3e42b6ULL, 0x597f299cfc657e2aULL, 0x5fcb6fab3ad6faecULL, 0x6c44198c4a475817ULL};
 
-EDG_HD u64 ror64(u64 x, int n) { return (x >> n) | (x << (64 - n)); }
+// rotate right by a compile-time constant: two funnel shifts on the device (the generic expression compiles to five
+// shift / multiply instructions per rotate)
+EDG_HD u64 ror64(u64 x, int n) {
+#if defined(__CUDA_ARCH__)
+    const u32 lo = (u32)x, hi = (u32)(x >> 32);
+    const u32 a = n < 32 ? lo : hi, b = n < 32 ? hi : lo;             // (b:a) >> (n mod 32) gives the low word, (a:b) the high
+    const u32 rl = __funnelshift_r(a, b, (u32)n & 31u), rh = __funnelshift_r(b, a, (u32)n & 31u);
+    return ((u64)rh << 32) | rl;
+#else
+    return (x >> n) | (x << (64 - n));
+#endif
+}
 
 EDG_HD u32 bswap32(u32 x) {
 #if defined(__CUDA_ARCH__)
