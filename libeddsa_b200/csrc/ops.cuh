@@ -251,14 +251,14 @@ EDG_HD void x25519_base_op(u32 out[8], const u32 scalar[8], const u32 *comb) {
 
 // ------------------------------------------------------------------------------------------------
 // Verify.                                                              [ed25519_verify, ed25519-sha512.c:148-181]
-// C = S*B + t*(-A) by Straus with fixed signed 4-bit windows over both scalars (uniform control
-// flow across the warp; the reference's vartime JSF chain ed.c:455-507 computes the same group
-// element for every on-curve A because the addition law is complete).
-//   qtab : this thread's scratch for 0..8 times (-A) in cached form, 9 x 32 words
-//   wtab : window table of the base point, e * B for e = 0 .. 2^(EDG_BWIN-1) in affine precomputed form
-//          (24 words each), built once per device by wtab_build8 and resident in L2: B is fixed, so its
-//          scalar is cut into signed EDG_BWIN-bit digits — 16 additions per signature instead of the 64
-//          a 4-bit window needs (the reference's JSF chain spends ~85 on B, ed.c:479-506).
+// The reference computes C = S*B + t*(-A) with a vartime JSF chain (ed.c:455-507) and compares encode(C) with the
+// first 32 signature bytes.  Here the same decision is taken by a Straus multi-scalar multiplication with fixed
+// signed windows (uniform control flow across the warp; the addition law is complete, so any schedule yields
+// the same group element for on-curve inputs) over HALF-SIZE scalars — see ed25519_verify_front / _loop below.
+//   wtab : window tables of the base point, e * B and e * 2^128 B for e = 0 .. 2^(EDG_BWIN-1) in affine
+//          precomputed form (24 words per entry), built once per device by wtab_base / wtab_build8 and resident
+//          in L2: B is fixed, so its scalar is cut into signed EDG_BWIN-bit digits — 16 additions per signature
+//          instead of the 64 a 4-bit window needs (the reference's JSF chain spends ~85 on B, ed.c:479-506).
 // ------------------------------------------------------------------------------------------------
 #ifndef EDG_BWIN
 #define EDG_BWIN 16
