@@ -85,6 +85,8 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_
                                                    const unsigned long long *off, unsigned long long fixed_len) {
     extern __shared__ __align__(16) u32 s_comb[];
     constexpr int TILE = kThreads * EDG_BATCH;
+    constexpr int kTileBits = TILE == 512 ? 9 : TILE == 1024 ? 10 : TILE == 2048 ? 11 : 12;
+    static_assert(TILE == (1 << kTileBits), "tile size must be a power of two");
     __shared__ u32 s_key[RAGGED ? TILE : 1];
     stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
     const size_t T = (size_t)gridDim.x * blockDim.x;
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_
             if (round < full) { i0 = (round * gridDim.x + blockIdx.x) * TILE; lim = i0 + TILE; }
             else { i0 = rem0 + blockIdx.x * share; lim = i0 + share < n ? i0 + share : n; }
             __syncthreads();                                   // the previous tile's keys are no longer needed
-            for (int e = threadIdx.x; e < TILE; e += blockDim.x) s_key[e] = i0 < lim ? ragged_key<10>(off, i0, e, lim) : 0xffffffffu;
+            for (int e = threadIdx.x; e < TILE; e += blockDim.x) s_key[e] = i0 < lim ? ragged_key<kTileBits>(off, i0, e, lim) : 0xffffffffu;
             block_sort_u32<TILE>(s_key);
         }
         auto op_index = [&](int k) -> size_t {
