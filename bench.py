@@ -52,9 +52,19 @@ PROD_M, PROD_S = 72, 44              # wide multiplies per field multiplication 
 # this engine executes (tests/test_host_sim.py::test_field_op_counts pins them)
 REF_FM = {"verify": (2291, 1514), "sign": (506, 254), "genpub": (506, 254), "x25519_base": (505, 254), "x25519": (1292, 1278)}
 OURS_FM_SINGLE = {"sign": (461, 254), "genpub": (461, 254), "x25519_base": (460, 254), "x25519": (1283, 1272)}
-# the kernels share one inversion (254 S + 11 M) among EDG_BATCH = 16 operations of a thread, +3 M per operation
-EDG_BATCH = 16
-OURS_FM = {op: (m - 11 + 11 / EDG_BATCH + 3, s_ - 254 + 254 / EDG_BATCH) for op, (m, s_) in OURS_FM_SINGLE.items()}
+# the kernels share one inversion (254 S + 11 M) among up to EDG_BATCH = 32 operations of a thread, +3 M per operation;
+# a thread of the persistent grid gets n / (resident threads) operations, so at 2^20 per GPU the share is 14..28
+EDG_BATCH = 32
+RESIDENT_THREADS = {"sign": 2 * 148 * 128, "genpub": 3 * 148 * 128, "x25519_base": 3 * 148 * 128, "x25519": 4 * 148 * 128}   # blocks/SM by registers
+
+
+def ours_fm(op, n=1 << 20):
+    m, s_ = OURS_FM_SINGLE[op]
+    share = max(1.0, min(float(EDG_BATCH), n / RESIDENT_THREADS[op]))
+    return (m - 11 + 11 / share + 3, s_ - 254 + 254 / share)
+
+
+OURS_FM = {op: ours_fm(op) for op in RESIDENT_THREADS}
 
 
 def verify_fm(nwin):

@@ -23,7 +23,7 @@ namespace edg {
 // compare) — which removes 7/8 of the inversions.  The single-operation functions below (used by the
 // host-side unit tests) are front + fe_inv + back, so both paths execute the same code.
 #ifndef EDG_BATCH
-#define EDG_BATCH 16     /* measured: 8 -> 16 gives +1.5 % on the fixed-base kernels, +0.6 % on x25519; 4 loses 3 % */
+#define EDG_BATCH 32     /* measured at 2^20: 8 -> 16 -> 32 gives +1.5 % and +1.7 % on genpub / x25519_base, +1.4 % and +0.7 % on sign */
 #endif
 #if EDG_BATCH < 8
 #error "EDG_BATCH must be at least 8 (wtab_build8 shares one inversion among 8 table entries)"
