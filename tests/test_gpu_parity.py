@@ -211,6 +211,44 @@ def test_random_differential_medium(ed, cpu):
     assert (ed.x25519_base_batch(sec) == cpu.x25519_base(sec)).all()
 
 
+def test_mutation_fuzz_verify_large(ed, cpu):
+    """2^17 signatures, three quarters of them mutated in one of twelve ways (bit flips in R / S / A / message, S + kL,
+    S := 0 or L, non-canonical or small-order R, R of another signature, small-order / non-canonical / sign-flipped A,
+    truncated hash input): every decision must equal the reference's (both accept-quirks and rejects occur)."""
+    import edmodel as em
+    rng = np.random.default_rng(1234)
+    n = 1 << 17
+    sec, msgs = rand_bytes(rng, n, 32), rand_bytes(rng, n, 48)
+    pub = ed.ed25519_genpub_batch(sec)
+    sig = ed.ed25519_sign_batch(sec, pub, msgs, fixed_len=48)
+    L = em.L
+    small = [np.frombuffer(em.enc(p), np.uint8) for p in em.small_order_points()]
+    small_nc = [np.frombuffer(em.enc(p, noncanonical=True), np.uint8) for p in em.small_order_points() if p[1] < 19]
+    cls = rng.integers(0, 16, n)                                # 12..15: left valid
+    for i in np.nonzero(cls < 12)[0]:
+        c = cls[i]
+        if c == 0: sig[i, rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+        elif c == 1: sig[i, 32 + rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+        elif c == 2: pub[i, rng.integers(0, 32)] ^= 1 << rng.integers(0, 8)
+        elif c == 3: msgs[i, rng.integers(0, 48)] ^= 1 << rng.integers(0, 8)
+        elif c == 4:
+            v = int.from_bytes(sig[i, 32:].tobytes(), "little") + int(rng.integers(1, 16)) * L
+            if v < 2**256: sig[i, 32:] = np.frombuffer(v.to_bytes(32, "little"), np.uint8)
+        elif c == 5: sig[i, 32:] = np.frombuffer((0 if rng.integers(0, 2) else L).to_bytes(32, "little"), np.uint8)
+        elif c == 6: sig[i, :32] = small_nc[rng.integers(0, len(small_nc))] if rng.integers(0, 2) else 0xff
+        elif c == 7: sig[i, :32] = small[rng.integers(0, 8)]
+        elif c == 8: sig[i, :32] = sig[(i + 1) % n, :32]
+        elif c == 9: pub[i] = small[rng.integers(0, 8)]
+        elif c == 10: pub[i, 31] ^= 0x80
+        elif c == 11: pub[i] = small_nc[rng.integers(0, len(small_nc))]
+    got = ed.ed25519_verify_batch(sig, pub, msgs, fixed_len=48)
+    want = cpu.verify(sig, pub, msgs, fixed_len=48)
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, [(int(i), int(cls[i]), int(got[i]), int(want[i])) for i in bad[:10]]
+    assert want[cls >= 12].all() and want[cls == 4].all()        # valid rows and S + kL rows are accepted
+    assert 0.25 * n < want.sum() < 0.45 * n
+
+
 def test_s_plus_kl_is_accepted(ed):
     """SURVEY Q1 as a property: S + kL verifies for every k with S + kL < 2^256."""
     rng = np.random.default_rng(500)
