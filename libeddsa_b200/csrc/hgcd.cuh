@@ -53,7 +53,80 @@ EDG_HD u32 hg_extract32(const u32 x[8], int s) {
     return (u32)(((((u64)hi) << 32) | lo) >> sh);
 }
 
-// out = a x - b y  modulo 2^(32 W): two's complement W-word values, small non-negative multipliers
+// out = a x - b y  modulo 2^(32 W): two's complement W-word values, small non-negative multipliers.
+// Device form: a x = E + 2^32 O with E the products of the even words and O those of the odd words — the 64-bit
+// products inside E (and inside O) do not overlap, so all of them are independent wide multiplies without an
+// addend; then three carry chains (E + O for both terms, and the difference).  The portable form below it (host
+// build of the tests) computes the same value word by word.
+#if defined(__CUDA_ARCH__)
+template <int W> __device__ __forceinline__ void hg_lin(u32 *out, const u32 *x, u32 a, const u32 *y, u32 b);
+
+// t[0..W) = low W words of m * v   (W = 8 or 6)
+template <int W> __device__ __forceinline__ void hg_mul1(u32 *t, const u32 *v, u32 m) {
+    u32 e[W], o[W];                                        // o[k] = word k of 2^32 O (o[0] = 0)
+#pragma unroll
+    for (int i = 0; i < W; i += 2) { const u64 p = mulw(m, v[i]); e[i] = (u32)p; e[i + 1] = (u32)(p >> 32); }
+    o[0] = 0;
+#pragma unroll
+    for (int i = 1; i < W; i += 2) {
+        if (i + 1 < W) { const u64 p = mulw(m, v[i]); o[i] = (u32)p; o[i + 1] = (u32)(p >> 32); }
+        else o[i] = m * v[i];
+    }
+    t[0] = e[0];
+    if (W == 8)
+        asm("add.cc.u32 %0, %7, %14; addc.cc.u32 %1, %8, %15; addc.cc.u32 %2, %9, %16; addc.cc.u32 %3, %10, %17; "
+            "addc.cc.u32 %4, %11, %18; addc.cc.u32 %5, %12, %19; addc.u32 %6, %13, %20;"
+            : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(e[6]), "r"(e[7]),
+              "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]));
+    else
+        asm("add.cc.u32 %0, %5, %10; addc.cc.u32 %1, %6, %11; addc.cc.u32 %2, %7, %12; addc.cc.u32 %3, %8, %13; addc.u32 %4, %9, %14;"
+            : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5])
+            : "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(e[4]), "r"(e[5]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]));
+}
+
+template <> __device__ __forceinline__ void hg_lin<8>(u32 *out, const u32 *x, u32 a, const u32 *y, u32 b) {
+    u32 p[8], q[8];
+    hg_mul1<8>(p, x, a);
+    hg_mul1<8>(q, y, b);
+    asm("sub.cc.u32 %0, %8, %16; subc.cc.u32 %1, %9, %17; subc.cc.u32 %2, %10, %18; subc.cc.u32 %3, %11, %19; "
+        "subc.cc.u32 %4, %12, %20; subc.cc.u32 %5, %13, %21; subc.cc.u32 %6, %14, %22; subc.u32 %7, %15, %23;"
+        : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5]), "=r"(out[6]), "=r"(out[7])
+        : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(p[6]), "r"(p[7]),
+          "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]), "r"(q[6]), "r"(q[7]));
+}
+template <> __device__ __forceinline__ void hg_lin<6>(u32 *out, const u32 *x, u32 a, const u32 *y, u32 b) {
+    u32 p[6], q[6];
+    hg_mul1<6>(p, x, a);
+    hg_mul1<6>(q, y, b);
+    asm("sub.cc.u32 %0, %6, %12; subc.cc.u32 %1, %7, %13; subc.cc.u32 %2, %8, %14; subc.cc.u32 %3, %9, %15; "
+        "subc.cc.u32 %4, %10, %16; subc.u32 %5, %11, %17;"
+        : "=r"(out[0]), "=r"(out[1]), "=r"(out[2]), "=r"(out[3]), "=r"(out[4]), "=r"(out[5])
+        : "r"(p[0]), "r"(p[1]), "r"(p[2]), "r"(p[3]), "r"(p[4]), "r"(p[5]), "r"(q[0]), "r"(q[1]), "r"(q[2]), "r"(q[3]), "r"(q[4]), "r"(q[5]));
+}
+
+// x = -x over W words (W = 8 or 6): one borrow chain from zero
+template <int W> __device__ __forceinline__ void hg_neg(u32 *x) {
+    if (W == 8)
+        asm("sub.cc.u32 %0, 0, %0; subc.cc.u32 %1, 0, %1; subc.cc.u32 %2, 0, %2; subc.cc.u32 %3, 0, %3; "
+            "subc.cc.u32 %4, 0, %4; subc.cc.u32 %5, 0, %5; subc.cc.u32 %6, 0, %6; subc.u32 %7, 0, %7;"
+            : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]), "+r"(x[6]), "+r"(x[7]));
+    else
+        asm("sub.cc.u32 %0, 0, %0; subc.cc.u32 %1, 0, %1; subc.cc.u32 %2, 0, %2; subc.cc.u32 %3, 0, %3; subc.cc.u32 %4, 0, %4; subc.u32 %5, 0, %5;"
+            : "+r"(x[0]), "+r"(x[1]), "+r"(x[2]), "+r"(x[3]), "+r"(x[4]), "+r"(x[5]));
+}
+
+// 1 if x < y (8-word unsigned): the borrow out of x - y
+__device__ __forceinline__ u32 hg_less8(const u32 x[8], const u32 y[8]) {
+    u32 d, bw;
+    asm("sub.cc.u32 %0, %2, %10; subc.cc.u32 %0, %3, %11; subc.cc.u32 %0, %4, %12; subc.cc.u32 %0, %5, %13; "
+        "subc.cc.u32 %0, %6, %14; subc.cc.u32 %0, %7, %15; subc.cc.u32 %0, %8, %16; subc.cc.u32 %0, %9, %17; subc.u32 %1, 0, 0;"
+        : "=&r"(d), "=r"(bw)
+        : "r"(x[0]), "r"(x[1]), "r"(x[2]), "r"(x[3]), "r"(x[4]), "r"(x[5]), "r"(x[6]), "r"(x[7]),
+          "r"(y[0]), "r"(y[1]), "r"(y[2]), "r"(y[3]), "r"(y[4]), "r"(y[5]), "r"(y[6]), "r"(y[7]));
+    return bw & 1u;
+}
+#else
 template <int W>
 EDG_HD void hg_lin(u32 *out, const u32 *x, u32 a, const u32 *y, u32 b) {
     u64 ca = 0, cb = 0;
@@ -91,6 +164,7 @@ EDG_HD u32 hg_less8(const u32 x[8], const u32 y[8]) {
     }
     return borrow;
 }
+#endif
 
 // (rho, tau): tau = rho * t (mod 8L), rho odd, rho = (rho_neg ? -1 : 1) * rho_abs.  t < L.
 // Normal case: rho_abs < 2^160 (typically < 2^129), tau < 2^128.  Fallback: rho = 1, tau = t.
