@@ -429,15 +429,30 @@ EDG_FE_MUL void fe_sq(fe &r, const fe &a) {
 
 // r = a * 121665 mod p.                     [reference: fld_scale, fld.c:184/:430; only s = 121665 is used, x25519.c:77]
 EDG_HD void fe_mul121665(fe &r, const fe &a) {
-    u64 c = 0;
-    u32 t[8];
+    u32 t[8], c;
+#if defined(__CUDA_ARCH__)
+    // eight INDEPENDENT products (the C loop below compiles to a serial chain of wide multiplies glued by moves),
+    // then one carry chain: word j = lo(p_j) + hi(p_{j-1})
+    u64 p[8];
 #pragma unroll
+    for (int j = 0; j < 8; j++) p[j] = mulw(a.v[j], 121665u);
+    t[0] = (u32)p[0];
+    asm("add.cc.u32 %0, %8, %15; addc.cc.u32 %1, %9, %16; addc.cc.u32 %2, %10, %17; addc.cc.u32 %3, %11, %18; "
+        "addc.cc.u32 %4, %12, %19; addc.cc.u32 %5, %13, %20; addc.cc.u32 %6, %14, %21; addc.u32 %7, %22, 0;"
+        : "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(c)
+        : "r"((u32)p[1]), "r"((u32)p[2]), "r"((u32)p[3]), "r"((u32)p[4]), "r"((u32)p[5]), "r"((u32)p[6]), "r"((u32)p[7]),
+          "r"((u32)(p[0] >> 32)), "r"((u32)(p[1] >> 32)), "r"((u32)(p[2] >> 32)), "r"((u32)(p[3] >> 32)), "r"((u32)(p[4] >> 32)),
+          "r"((u32)(p[5] >> 32)), "r"((u32)(p[6] >> 32)), "r"((u32)(p[7] >> 32)));
+#else
+    u64 cc = 0;
     for (int j = 0; j < 8; j++) {
-        const u64 p = mulw(a.v[j], 121665u) + c;
+        const u64 p = mulw(a.v[j], 121665u) + cc;
         t[j] = (u32)p;
-        c = p >> 32;
+        cc = p >> 32;
     }
-    const u32 c2 = addw8(t, (u32)c * 38u);             // c < 2^17
+    c = (u32)cc;
+#endif
+    const u32 c2 = addw8(t, c * 38u);                   // c < 2^17
     t[0] += 38u & (0u - c2);
 #pragma unroll
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
