@@ -12,17 +12,17 @@ using namespace edg;
 #ifndef EDG_VERIFY_WAVES
 #define EDG_VERIFY_WAVES 4  /* waves of resident threads per pass: sizes the per-signature records in scratch */
 #endif
+#ifndef EDG_LB_VERIFY
+#define EDG_LB_VERIFY 4     /* front kernel: min resident blocks per SM the register allocator must allow: 128 registers, 4 warps
+                               per scheduler */
+#endif
 #ifndef EDG_VTHREADS
-#define EDG_VTHREADS EDG_THREADS   /* block size of the window-loop kernel */
+#define EDG_VTHREADS EDG_THREADS   /* block size of the window-loop kernel (64 .. 256 threads and 2 .. 8 resident blocks all land
+                                      within 2 % of each other, profiles/r01_pipe_microbench.md) */
 #endif
 #ifndef EDG_LB_VLOOP
-#define EDG_LB_VLOOP EDG_LB_VERIFY_
+#define EDG_LB_VLOOP EDG_LB_VERIFY
 #endif
-#ifndef EDG_LB_VERIFY
-#define EDG_LB_VERIFY 4     /* front kernel: min resident blocks per SM the register allocator must allow: 128 registers, 4 warps/SMSP
-                               (measured +4 % over 3 blocks, profiles/r01_summary.md) */
-#endif
-#define EDG_LB_VERIFY_ EDG_LB_VERIFY
 namespace {
 constexpr int kVThreads = EDG_VTHREADS;
 
