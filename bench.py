@@ -51,11 +51,11 @@ PROD_M, PROD_S = 72, 44              # wide multiplies per field multiplication 
 # field operations per op: reference counts (instrumented reference) and the counts
 # this engine executes (tests/test_host_sim.py::test_field_op_counts pins them)
 REF_FM = {"verify": (2291, 1514), "sign": (506, 254), "genpub": (506, 254), "x25519_base": (505, 254), "x25519": (1292, 1278)}
-OURS_FM_SINGLE = {"sign": (461, 254), "genpub": (461, 254), "x25519_base": (460, 254), "x25519": (1283, 1272)}
+OURS_FM_SINGLE = {"sign": (369, 254), "genpub": (369, 254), "x25519_base": (368, 254), "x25519": (1283, 1272)}   # 51-row signed radix-32 comb
 # the kernels share one inversion (254 S + 11 M) among up to EDG_BATCH = 32 operations of a thread, +3 M per operation;
 # a thread of the persistent grid gets n / (resident threads) operations, so at 2^20 per GPU the share is 14..28
 EDG_BATCH = 32
-RESIDENT_THREADS = {"sign": 2 * 148 * 128, "genpub": 3 * 148 * 128, "x25519_base": 3 * 148 * 128, "x25519": 4 * 148 * 128}   # blocks/SM by registers
+RESIDENT_THREADS = {"sign": 2 * 148 * 256, "genpub": 2 * 148 * 256, "x25519_base": 2 * 148 * 256, "x25519": 4 * 148 * 128}   # k_comb: 2 x 256 threads per SM
 
 
 def ours_fm(op, n=1 << 20):
@@ -230,6 +230,7 @@ def run_ours(args):
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=dev)
+            gloo = dist.new_group(backend="gloo")
             dist.barrier()
             torch.cuda.synchronize()
         finally:
@@ -337,7 +338,78 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     assert bool(h_ok.all().item())
     e2e_value = world * n * K / e2e_s
+    # ---- the same from ordinary (pageable) memory: the library stages through its pinned slots ------------------
+    p_sig, p_pub, p_msg, p_ok = np.array(h_sig.numpy()), np.array(h_pub.numpy()), np.array(h_msg.numpy()), np.empty(n, np.uint8)
+    ap = lambda a: ctypes.c_void_p(a.ctypes.data)
+    Kx = min(K, 5)
+
+    def e2e_pageable_step():
+        rc = L.ed25519_verify_batch(n, ap(p_ok), ap(p_sig), ap(p_pub), ap(p_msg), None, 64)
+        if rc:
+            raise RuntimeError(f"ed25519_verify_batch failed: {rc} {L.eddsa_b200_last_error()}")
+
+    def wall(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0)
+
+    pg_s = wall(e2e_pageable_step, Kx, 1)
+    assert p_ok.all()
+    also["e2e_pageable"] = {"value": world * n * Kx / pg_s, "unit": UNIT, "api": "ed25519_verify_batch, ordinary (malloc) host buffers: staged through the "
+                            "library's pinned slots with memcpy", "ms_per_step": pg_s / Kx * 1e3}
+    del p_sig, p_pub, p_msg
+
+    # ---- BASELINE config 5's shape end to end: 1 KB messages, 10 % corrupted, pinned host buffers ----------------
+    mlen = 1024
+    g1 = torch.Generator(device=dev)
+    g1.manual_seed(0x5EED0005 + rank)
+    d_msg1k = torch.randint(0, 256, (n, mlen), dtype=torch.uint8, device=dev, generator=g1)
+    ed.ed25519_sign_batch_dev(d_sig, d_sec, d_pub, d_msg1k, fixed_len=mlen)
+    bad = torch.arange(0, n, 10, device=dev)
+    d_sig[bad, 3 + (bad % 40)] ^= 1
+    h_msg1k = torch.empty((n, mlen), dtype=torch.uint8, pin_memory=True)
+    h_msg1k.copy_(d_msg1k)
+    h_sig1k = torch.empty((n, 64), dtype=torch.uint8, pin_memory=True)
+    h_sig1k.copy_(d_sig)
+    torch.cuda.synchronize()
+    del d_msg1k
+
+    def e2e_1kb_step():
+        rc = L.ed25519_verify_batch(n, vp(h_ok), vp(h_sig1k), vp(h_pub), vp(h_msg1k), None, mlen)
+        if rc:
+            raise RuntimeError(f"ed25519_verify_batch failed: {rc} {L.eddsa_b200_last_error()}")
+
+    kb_s = wall(e2e_1kb_step, Kx, 1)
+    assert int(h_ok.sum().item()) == n - len(bad)
+    kb_bytes = n * (64 + 32 + mlen)
+    also["e2e_1kb"] = {"value": world * n * Kx / kb_s, "unit": UNIT, "api": "ed25519_verify_batch (host buffers, pinned), 1024-byte messages, 10 % of the signatures corrupted",
+                       "ms_per_step": kb_s / Kx * 1e3, "h2d_bytes_per_step": kb_bytes, "h2d_gbs_per_gpu": kb_bytes * Kx / kb_s / 1e9,
+                       "note": "copy-bound: every signature brings 1 120 bytes over PCIe; compare h2d_gbs_per_gpu with also.inproc.copy_bandwidth"}
+    del h_msg1k, h_sig1k
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- single operations of eddsa.h (batch of one on the GPU) next to the reference's CPU time ------------------
+    if rank == 0:
+        also["single_op_latency_us"] = single_op_latency(ed, h_sec.numpy(), h_pub.numpy(), h_sig.numpy(), h_msg.numpy(), h_pts.numpy())
+
+    # ---- the library's own multi-device path on BASELINE configs 4 and 5 (one process, all N devices) ------------
+    # rank 0 runs tools/inproc_bench.py as a subprocess; the other ranks wait on a CPU (gloo) barrier so that their
+    # GPUs are idle (an NCCL barrier would spin a kernel on them)
+    torch.cuda.synchronize()
+    del flush
+    torch.cuda.empty_cache()
+    ed.shutdown()
+    if world > 1:
+        dist.barrier()
+    if rank == 0 and not args.no_inproc:
+        also["inproc"] = run_inproc(world)
+    if world > 1:
+        dist.barrier(group=gloo)
 
     if rank == 0:
         # ---- roofline of the dominant kernel (k_verify) ---------------------------------------------
@@ -383,9 +455,59 @@ def run_ours(args):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def single_op_latency(ed, sec, pub, sig, msg, pts, calls=300):
+    """Median wall time of one call of each eddsa.h function (a batch of one on the GPU: H2D, kernels, D2H, synchronise)
+    and of the same call into the reference's CPU library."""
+    import ctypes
+    from cpu_ref import have_reference, reference_path
+    ours = ed.lib()
+    ref = ctypes.CDLL(reference_path()) if have_reference() else None
+    out = ctypes.create_string_buffer(64)
+    rows = [(sec[i].tobytes(), pub[i].tobytes(), sig[i].tobytes(), msg[i].tobytes(), pts[i].tobytes()) for i in range(64)]
+
+    def med(fn):
+        for i in range(30):
+            fn(rows[i % 64])
+        ts = []
+        for i in range(calls):
+            r = rows[i % 64]
+            t0 = time.perf_counter()
+            fn(r)
+            ts.append(time.perf_counter() - t0)
+        return round(statistics.median(ts) * 1e6, 1)
+
+    res = {}
+    for name, lib in (("gpu", ours), ("reference_cpu", ref)):
+        if lib is None:
+            continue
+        lib.ed25519_verify.restype = ctypes.c_bool
+        res[name] = {
+            "ed25519_genpub": med(lambda r: lib.ed25519_genpub(out, r[0])),
+            "ed25519_sign_64B": med(lambda r: lib.ed25519_sign(out, r[0], r[1], r[3], ctypes.c_size_t(64))),
+            "ed25519_verify_64B": med(lambda r: lib.ed25519_verify(r[2], r[1], r[3], ctypes.c_size_t(64))),
+            "x25519": med(lambda r: lib.x25519(out, r[0], r[4])),
+            "x25519_base": med(lambda r: lib.x25519_base(out, r[0])),
+        }
+    res["note"] = "median of %d calls; the GPU figure is one thread of one kernel chain plus two copies and a synchronise — latency-bound callers should batch" % calls
+    return res
+
+
+def run_inproc(world):
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "inproc_bench.py"), "--devices", str(world)]
+    drop = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "MASTER_ADDR", "MASTER_PORT", "EDDSA_B200_DEVICES", "OMP_NUM_THREADS")
+    env = {k: v for k, v in os.environ.items() if k not in drop and not k.startswith("TORCHELASTIC")}
+    try:
+        res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+        for line in reversed(res.stdout.strip().splitlines()):
+            if line.startswith("{"):
+                return json.loads(line)
+        return {"error": (res.stderr or res.stdout)[-600:]}
+    except Exception as e:                                       # noqa: BLE001 — the headline line must still be printed
+        return {"error": repr(e)}
 
 
 def ncu_traffic(n):
@@ -424,6 +546,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-log2", type=int, default=20)
+    ap.add_argument("--no-inproc", action="store_true", help="skip the in-library multi-device leg (configs 4 and 5 at 2^24)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

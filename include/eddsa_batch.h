@@ -18,8 +18,15 @@
  * the caller's memory.  Caller buffers that are already page-locked are copied from directly.
  *
  * Device-buffer functions (…_batch_dev): all pointers are device pointers on the CURRENT CUDA device,
- * 16-byte aligned; the work is enqueued on `stream` (a cudaStream_t, NULL = default stream) and the
- * call returns without synchronising.
+ * 16-byte aligned (the `ok` flags: any alignment); the work is enqueued on `stream` (a cudaStream_t,
+ * NULL = default stream) and the call returns without synchronising.  Kernel scratch (verify: 2.4 KB
+ * per signature of a pass of at most 303 104; sign / genpub: 64 / 32 bytes per operation of a pass
+ * of at most 2^21) is taken from a stream-ordered memory pool on `stream` and returned to it by the
+ * same call, so any number of streams may be used and nothing synchronises.
+ *
+ * Secret keys: staging memory of the host-buffer functions that carried secret inputs (sec, scalar)
+ * or secret outputs (x25519 shared secrets, converted secret keys) is zeroed when its chunk completes,
+ * on the host and on the device; kernel scratch that carried secret scalars is zeroed by the kernels.
  *
  * Return value: 0 on success, otherwise a nonzero error code (a cudaError_t value, or
  * EDDSA_B200_EINVAL); on error the outputs are unspecified.  eddsa_b200_last_error() describes it.
@@ -76,13 +83,24 @@ EDDSA_DECL int eddsa_b200_set_device_count(int count);
 /* kernels launched by this library so far in this process (all devices) */
 EDDSA_DECL unsigned long long eddsa_b200_launch_count(void);
 /* diagnostic: one GF(2^255-19) operation per item, executed by the device field library (op: 0 mul,
- * 1 square, 2 add, 3 sub, 4 times 121665, 5 canonical form, 6 inverse, 7 power (p-5)/8, 8 negate);
+ * 1 square, 2 add, 3 sub, 4 times 121665, 5 canonical form, 6 inverse, 7 power (p-5)/8, 8 negate,
+ * 9 the kernels' shared inversion over each group of 32 consecutive items of a, 0 -> 0);
  * a, b, out are n x 32 little-endian bytes, any 256-bit values.  Used by the GPU unit tests. */
 EDDSA_DECL int eddsa_b200_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op);
+/* diagnostic: one operation modulo the group order L per item, executed by the device scalar library (op: 0
+ * out = (a + 2^256 b) mod L, 1 out = a mod L, 2 out = a b + c mod L); a, b, c, out are n x 32 bytes. */
+EDDSA_DECL int eddsa_b200_sc_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, const uint8_t *c, int op);
 /* diagnostic: copies the verify kernels' base-point window tables of the current device to `out`: table m (m = 0, 1)
  * holds e * 2^(128 m) * B for e = 0 .. 2^15 as 96-byte entries (y+x, y-x, 2dxy; canonical little-endian field
  * elements).  Returns the number of bytes written (2 x 32769 x 96) or 0 if `cap` is too small / on error. */
 EDDSA_DECL size_t eddsa_b200_verify_tables(uint8_t *out, size_t cap);
+/* diagnostic: copies the fixed-base comb table of the current device to `out`: rows x entries x 96 bytes, entry
+ * [j][k] = (k + 1) * 2^(W j) * B as (y+x, y-x, 2dxy) (W = 5: 51 rows x 16 entries).  Returns the bytes written or 0. */
+EDDSA_DECL size_t eddsa_b200_comb_table(uint8_t *out, size_t cap);
+/* diagnostic (tests of the secret-scrubbing contract): copies up to `len` bytes from the start of staging buffer
+ * `which` (0 host input, 1 device input, 2 host output, 3 device output) of pipeline slot `slot` (0..2) of the
+ * current device to `out`; returns the bytes copied (0 if that buffer does not exist yet). */
+EDDSA_DECL size_t eddsa_b200_debug_peek_staging(int which, int slot, uint8_t *out, size_t len);
 /* human-readable description of the last error seen by the calling thread ("" if none) */
 EDDSA_DECL const char *eddsa_b200_last_error(void);
 

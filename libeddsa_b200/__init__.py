@@ -65,7 +65,10 @@ def lib():
             "pk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
             "sk_ed25519_to_x25519_batch_dev": [sz, vp, vp, vp],
             "eddsa_b200_fe_selftest": [sz, vp, vp, vp, ip],
+            "eddsa_b200_sc_selftest": [sz, vp, vp, vp, vp, ip],
             "eddsa_b200_verify_tables": [vp, sz],
+            "eddsa_b200_comb_table": [vp, sz],
+            "eddsa_b200_debug_peek_staging": [ip, ip, vp, sz],
             "eddsa_b200_init": [],
             "eddsa_b200_device_count": [],
             "eddsa_b200_set_device_count": [ip],
@@ -76,6 +79,8 @@ def lib():
         L.eddsa_b200_shutdown.restype = None
         L.eddsa_b200_launch_count.restype = ctypes.c_ulonglong
         L.eddsa_b200_verify_tables.restype = ctypes.c_size_t
+        L.eddsa_b200_comb_table.restype = ctypes.c_size_t
+        L.eddsa_b200_debug_peek_staging.restype = ctypes.c_size_t
         L.eddsa_b200_last_error.restype = ctypes.c_char_p
         L.ed25519_verify.restype = ctypes.c_bool
         L.ed25519_verify.argtypes = [vp, vp, vp, sz]
@@ -202,6 +207,32 @@ def verify_tables():
     got = lib().eddsa_b200_verify_tables(_p(out), out.nbytes)
     if got != out.nbytes:
         raise EddsaB200Error(f"eddsa_b200_verify_tables returned {got}: " + lib().eddsa_b200_last_error().decode(errors="replace"))
+    return out
+
+
+def comb_table():
+    """Diagnostic: the device-built fixed-base comb table as a (rows, entries, 96) uint8 array."""
+    buf = np.empty(1 << 20, np.uint8)
+    got = lib().eddsa_b200_comb_table(_p(buf), buf.nbytes)
+    if got == 0 or got % 96:
+        raise EddsaB200Error(f"eddsa_b200_comb_table returned {got}: " + lib().eddsa_b200_last_error().decode(errors="replace"))
+    cells = got // 96
+    entries = 16 if cells % 16 == 0 and 255 // 5 + 1 == cells // 16 else 8       # W = 5: 51 x 16, W = 4: 64 x 8
+    return buf[:got].reshape(cells // entries, entries, 96).copy()
+
+
+def peek_staging(which, slot, length):
+    """Diagnostic: the first `length` bytes of a staging buffer of the current device (see eddsa_batch.h)."""
+    buf = np.zeros(length, np.uint8)
+    got = lib().eddsa_b200_debug_peek_staging(which, slot, _p(buf), length)
+    return buf[:got]
+
+
+def sc_selftest(a, b, c, op):
+    """Diagnostic: scalar operation `op` (0 reduce512, 1 reduce256, 2 muladd) on n x 32-byte operands on the device."""
+    a, b, c = _arr(a, 32, "a"), _arr(b, 32, "b"), _arr(c, 32, "c")
+    out = np.empty_like(a)
+    _check(lib().eddsa_b200_sc_selftest(len(a), _p(out), _p(a), _p(b), _p(c), op), "eddsa_b200_sc_selftest")
     return out
 
 

@@ -341,8 +341,6 @@ EDG_HD void fe_sub(fe &r, const fe &a, const fe &b) {
     for (int i = 0; i < 8; i++) r.v[i] = t[i];
 }
 
-EDG_HD void fe_sub4(fe &r, const fe &a, const fe &b) { fe_sub(r, a, b); }     // (no lazy limbs any more)
-
 // r = -a                                               [reference: fld_neg, fld.h:138]
 EDG_HD void fe_neg(fe &r, const fe &a) {
     fe z;
@@ -352,8 +350,6 @@ EDG_HD void fe_neg(fe &r, const fe &a) {
 
 // r = 2a                                               [reference: fld_scale2, fld.h:126]
 EDG_HD void fe_dbl(fe &r, const fe &a) { fe_add(r, a, a); }
-
-EDG_HD void fe_carry(fe &r, const fe &a) { fe_copy(r, a); }                   // kept for the point formulas' sake: nothing to carry
 
 // r = a * b mod p.  72 IMAD.WIDE.U32.                            [reference: fld_mul, fld.c:210 / :448]
 EDG_FE_MUL void fe_mul(fe &r, const fe &a, const fe &b) {

@@ -134,17 +134,18 @@ EDG_HD void ge_pre_cneg(ge_pre &q, u32 neg) {
     fe_select(q.xy2d, q.xy2d, nt, neg);
 }
 
-// Constant-time lookup of digit * (row point), digit in [-8, 7]; row = 8 entries x 24 words holding
-// 1P..8P.  Every entry is read and folded in with a mask; no branch or address depends on digit.
+// Constant-time lookup of digit * (row point), digit in [-ENTRIES, ENTRIES); row = ENTRIES entries x 24 words
+// holding 1P .. ENTRIES P.  Every entry is read and folded in with a mask; no branch or address depends on digit.
 //                                                                                 [scale16, ed.c:346-391]
+template <int ENTRIES>
 EDG_HD void ge_pre_select_ct(ge_pre &t, const u32 *row, int digit) {
     const u32 neg = ct_mask((u32)(digit >> 31));         // all-ones if digit < 0
-    const u32 absd = ((u32)digit ^ neg) - neg;           // 0..8
+    const u32 absd = ((u32)digit ^ neg) - neg;           // 0 .. ENTRIES
     u32 w[24];
 #pragma unroll
     for (int i = 0; i < 24; i++) w[i] = (i == 0 || i == 8) ? 1u : 0u;     // neutral element (1, 1, 0)
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < ENTRIES; k++) {
         const u32 m = ct_mask(0u - ((((absd ^ (u32)(k + 1)) - 1u) >> 31)));   // all-ones iff absd == k+1
 #if defined(__CUDA_ARCH__)
         // entry k starts at word 24k: 16-byte aligned -> 6 x 128-bit broadcast loads (same address in every lane)
@@ -162,28 +163,6 @@ EDG_HD void ge_pre_select_ct(ge_pre &t, const u32 *row, int digit) {
         for (int i = 0; i < 24; i++) w[i] ^= (w[i] ^ row[24 * k + i]) & m;
 #endif
     }
-#pragma unroll
-    for (int i = 0; i < 8; i++) { t.ypx.v[i] = w[i]; t.ymx.v[i] = w[8 + i]; t.xy2d.v[i] = w[16 + i]; }
-    ge_pre_cneg(t, neg);
-}
-
-// Variable-time (public data) lookup for the verify kernel: entry |digit| of a 9-entry table
-// (0 = neutral element), negated when digit < 0.  Entries are EDG_SMALL_STRIDE = 26 words apart (24
-// used): with 64-bit shared-memory loads the <= 9 distinct entries a warp touches then fall in
-// distinct bank pairs, so the lookup is conflict-free.
-#define EDG_SMALL_STRIDE 26
-EDG_HD void ge_pre_load(ge_pre &t, const u32 *tbl, int digit) {
-    const u32 neg = (u32)(digit >> 31);
-    const u32 absd = ((u32)digit ^ neg) - neg;
-    const u32 *e = tbl + EDG_SMALL_STRIDE * absd;
-    u32 w[24];
-#if defined(__CUDA_ARCH__)
-    const uint2 *e2 = reinterpret_cast<const uint2 *>(e);
-#pragma unroll
-    for (int i = 0; i < 12; i++) { const uint2 v = e2[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
-#else
-    for (int i = 0; i < 24; i++) w[i] = e[i];
-#endif
 #pragma unroll
     for (int i = 0; i < 8; i++) { t.ypx.v[i] = w[i]; t.ymx.v[i] = w[8 + i]; t.xy2d.v[i] = w[16 + i]; }
     ge_pre_cneg(t, neg);
@@ -219,7 +198,7 @@ EDG_HD u32 ge_frombytes(ge_p3 &p, const u32 in[8], bool negate, u32 *canonical =
     fe_mul(beta, u, t);                                  // beta = u v^3 (u v^7)^((p-5)/8)    ed.c:121-131
     fe_sq(chk, beta);
     fe_mul(chk, chk, v);                                 // v beta^2
-    fe_sub4(t, chk, u);
+    fe_sub(t, chk, u);
     const u32 is_root = 0u - fe_is_zero(t);              // v beta^2 == u                      ed.c:134-137
     fe_add(t, chk, u);
     const u32 is_jroot = 0u - fe_is_zero(t);             // v beta^2 == -u  <=>  v (j beta)^2 == u
@@ -251,15 +230,6 @@ EDG_HD void ge_affine_tobytes(u32 out[8], const fe &x, const fe &y) {
     fe_to_words(out, y);
     fe_canon(cx, x);
     out[7] |= (cx.v[0] & 1u) << 31;
-}
-
-// Extended point -> 32 bytes (one inversion, 254S + 13M).                       [ed_export, ed.c:155-169]
-EDG_HD void ge_tobytes(u32 out[8], const ge_p3 &p) {
-    fe zi, x, y;
-    fe_inv(zi, p.Z);
-    fe_mul(x, p.X, zi);
-    fe_mul(y, p.Y, zi);
-    ge_affine_tobytes(out, x, y);
 }
 
 }  // namespace edg

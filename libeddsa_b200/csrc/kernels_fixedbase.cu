@@ -1,147 +1,162 @@
 // Fixed-base kernels (sm_100a): ed25519_genpub, ed25519_sign, x25519_base and sk_ed25519_to_x25519.
-// One operation per thread; the 49 152-byte signed radix-16 comb table of B is staged once per
-// persistent block in shared memory and scanned with masks (constant time: no branch or address
-// depends on a secret).  Replaces ed25519-sha512.c:53-137, 243-256 and x25519.c:158-208.
-#define EDG_TABLE_QUAL __device__ const
-#define EDG_WANT_BASE_COMB
+// Replaces ed25519-sha512.c:53-137, 243-256 and x25519.c:158-208.
+//
+// The work of these operations is of two kinds that want different kernels:
+//   * the comb  x -> x * B  (+ shared inversion + encoding): bound by the integer multiplier.  ONE kernel, k_comb, serves
+//     all three operations.  The signed radix-2^W table of B (sc.cuh: EDG_COMB_W; built once per device by k_comb_base /
+//     k_comb_rows) is staged in shared memory once per persistent block and scanned with masks — constant time: no
+//     branch or address depends on a secret.  Small code, <= 128 registers: 4 warps per scheduler.
+//   * SHA-512 / arithmetic mod L (key expansion, nonce, challenge, S = r + t a): ALU-bound, no field arithmetic.  Small
+//     kernels of their own (k_expand_key, k_sign_nonce, k_sign_finish), one operation per thread; ragged batches are
+//     visited in tiles sorted by message length so that the lanes of a warp hash messages of similar length.
+// Secret scalars travel between the stages through a scratch buffer the last reader overwrites with zeros.
+// (Round 1 ran everything in one 240 KB kernel per operation at 188 / 161 registers: the multiplier pipe was 58-63 % busy.)
 #include "kernel_common.cuh"
 using namespace edg;
-#include "base_table.inc"
 
-#ifndef EDG_LB_X25519_BASE
-#define EDG_LB_X25519_BASE 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#ifndef EDG_COMB_THREADS
+#define EDG_COMB_THREADS 256
 #endif
-#ifndef EDG_LB_GENPUB
-#define EDG_LB_GENPUB 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#ifndef EDG_COMB_BLOCKS
+#define EDG_COMB_BLOCKS 2        /* resident blocks per SM: 2 x 256 threads x 128 registers, 2 x 78 KB of shared memory */
 #endif
-#ifndef EDG_LB_SIGN
-#define EDG_LB_SIGN 1     /* min resident blocks per SM the register allocator must allow (tuned, see profiles/) */
+#ifndef EDG_FIXEDBASE_PASS_LOG2
+#define EDG_FIXEDBASE_PASS_LOG2 21   /* operations per pass of the staged kernels: bounds the scratch (64 B per signature) */
+#endif
+#ifndef EDG_MSG_TILE
+#define EDG_MSG_TILE 2048        /* ragged batches: consecutive operations sorted by message length together */
 #endif
 namespace {
 
-constexpr int kCombBytes = EDG_BASE_COMB_WORDS * 4;      // 49 152
+constexpr int kCombThreads = EDG_COMB_THREADS;
+constexpr int kCombBytes = EDG_COMB_WORDS * 4;
+constexpr size_t kPass = (size_t)1 << EDG_FIXEDBASE_PASS_LOG2;
+constexpr int kMsgTile = EDG_MSG_TILE;
+constexpr int kMsgTileBits = kMsgTile == 512 ? 9 : kMsgTile == 1024 ? 10 : kMsgTile == 2048 ? 11 : 12;
+static_assert(kMsgTile == (1 << kMsgTileBits), "tile size must be a power of two between 512 and 4096");
 
-__global__ void __launch_bounds__(kThreads, EDG_LB_X25519_BASE) k_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar) {
+__device__ __forceinline__ void store_words8(u32 *dst, const u32 w[8]) {
+    uint4 *p = reinterpret_cast<uint4 *>(dst);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+__device__ __forceinline__ void wipe_words8(u32 *dst) {
+    volatile uint4 *p = reinterpret_cast<volatile uint4 *>(dst);
+    p[0].x = 0; p[0].y = 0; p[0].z = 0; p[0].w = 0; p[1].x = 0; p[1].y = 0; p[1].z = 0; p[1].w = 0;
+}
+
+// MODE 0: out[i] = Edwards encoding of scalars[i] * B, scalars already reduced mod L (from k_expand_key / k_sign_nonce)
+// MODE 1: out[i] = Montgomery u of (clamp(scalars[i]) mod L) * B for raw 32-byte scalars (x25519_base)
+// Every thread runs up to EDG_BATCH operations with one shared inversion (ops.cuh: fe_batch_inv).
+template <int MODE>
+__global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n, uint8_t *out, unsigned out_stride, u32 *scalars, int wipe,
+                                                                      const u32 *__restrict__ comb_g) {
     extern __shared__ __align__(16) u32 s_comb[];
-    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
+    stage_table(s_comb, comb_g, EDG_COMB_WORDS);
     const size_t T = (size_t)gridDim.x * blockDim.x;
     for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
-        fe N[EDG_BATCH], D[EDG_BATCH];
+        fe U[EDG_BATCH], V[MODE == 0 ? EDG_BATCH : 1], Z[EDG_BATCH];     // MODE 0: X, Y, Z;  MODE 1: Z + Y, -, Z - Y
         int cnt = 0;
 #pragma unroll 1
         for (int k = 0; k < EDG_BATCH; k++) {
             const size_t i = i0 + (size_t)k * T;
             if (i >= n) break;
-            u32 s[8];
-            load8(s, scalar, i);
-            x25519_base_front(N[k], D[k], s, s_comb);
-            cnt++;
-        }
-        fe_batch_inv(D, cnt);
-#pragma unroll 1
-        for (int k = 0; k < cnt; k++) {
-            u32 o[8];
-            x25519_back(o, N[k], D[k]);
-            store8(out, i0 + (size_t)k * T, o);
-        }
-        scrub(N, EDG_BATCH);
-        scrub(D, EDG_BATCH);
-    }
-}
-
-__global__ void __launch_bounds__(kThreads, EDG_LB_GENPUB) k_genpub(size_t n, uint8_t *pub, const uint8_t *sec) {
-    extern __shared__ __align__(16) u32 s_comb[];
-    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
-        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH];
-        int cnt = 0;
-#pragma unroll 1
-        for (int k = 0; k < EDG_BATCH; k++) {
-            const size_t i = i0 + (size_t)k * T;
-            if (i >= n) break;
-            ge_p3 A;
-            ed25519_genpub_front(A, sec + 32 * i, s_comb);
-            fe_copy(X[k], A.X); fe_copy(Y[k], A.Y); fe_copy(Z[k], A.Z);
-            cnt++;
-        }
-        fe_batch_inv(Z, cnt);
-#pragma unroll 1
-        for (int k = 0; k < cnt; k++) {
-            u32 o[8];
-            ge_tobytes_zinv(o, X[k], Y[k], Z[k]);
-            store8(pub, i0 + (size_t)k * T, o);
-        }
-        scrub(X, EDG_BATCH);
-        scrub(Y, EDG_BATCH);
-        scrub(Z, EDG_BATCH);
-    }
-}
-
-// RAGGED = the batch has an offsets array: tiles of kThreads x EDG_BATCH consecutive signatures, visited in order of
-// message length (kernel_common.cuh: block_sort_u32); otherwise the grid-stride mapping of the other kernels.
-template <bool RAGGED>
-__global__ void __launch_bounds__(kThreads, EDG_LB_SIGN) k_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
-                                                   const unsigned long long *off, unsigned long long fixed_len) {
-    extern __shared__ __align__(16) u32 s_comb[];
-    constexpr int TILE = kThreads * EDG_BATCH;
-    constexpr int kTileBits = TILE == 512 ? 9 : TILE == 1024 ? 10 : TILE == 2048 ? 11 : 12;
-    static_assert(TILE == (1 << kTileBits), "tile size must be a power of two");
-    __shared__ u32 s_key[RAGGED ? TILE : 1];
-    stage_table(s_comb, BASE_COMB, EDG_BASE_COMB_WORDS);
-    const size_t T = (size_t)gridDim.x * blockDim.x;
-    // RAGGED: full rounds of one TILE per block, then the remainder split evenly over the blocks (smaller tiles), so
-    // that the last round costs every block the same; otherwise one grid-stride round per EDG_BATCH x T signatures
-    const size_t full = RAGGED ? n / ((size_t)gridDim.x * TILE) : 0;
-    const size_t rem0 = full * gridDim.x * TILE;
-    const size_t share = RAGGED ? ((n - rem0 + gridDim.x - 1) / gridDim.x + 31) / 32 * 32 : 0;     // <= TILE
-    const size_t rounds = RAGGED ? full + (n > rem0 ? 1 : 0) : 0;
-    size_t round = 0, i0 = RAGGED ? 0 : (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; RAGGED ? round < rounds : i0 < n; round++, i0 += T * EDG_BATCH) {
-        if (RAGGED) {
-            size_t lim;                                        // tile [i0, lim)
-            if (round < full) { i0 = (round * gridDim.x + blockIdx.x) * TILE; lim = i0 + TILE; }
-            else { i0 = rem0 + blockIdx.x * share; lim = i0 + share < n ? i0 + share : n; }
-            __syncthreads();                                   // the previous tile's keys are no longer needed
-            for (int e = threadIdx.x; e < TILE; e += blockDim.x) s_key[e] = i0 < lim ? ragged_key<kTileBits>(off, i0, e, lim) : 0xffffffffu;
-            block_sort_u32<TILE>(s_key);
-        }
-        auto op_index = [&](int k) -> size_t {
-            if (!RAGGED) return i0 + (size_t)k * T;
-            const u32 key = s_key[threadIdx.x + kThreads * k];
-            return key == 0xffffffffu ? n : i0 + (key & (TILE - 1));
-        };
-        fe X[EDG_BATCH], Y[EDG_BATCH], Z[EDG_BATCH], AR[2 * EDG_BATCH];     // AR: secret scalar a and nonce r of each signature
-        int cnt = 0;
-#pragma unroll 1
-        for (int k = 0; k < EDG_BATCH; k++) {
-            const size_t i = op_index(k);
-            if (i >= n) break;
-            const uint8_t *m; u64 len;
-            msg_of(m, len, msgs, off, fixed_len, i);
+            u32 x[8];
+            load_words8(x, scalars + 8 * i);
+            if (wipe) wipe_words8(scalars + 8 * i);            // (public flag) this kernel is the last reader of the scalar
+            if (MODE == 1) {
+                u32 e[8];
+#pragma unroll
+                for (int w = 0; w < 8; w++) e[w] = x[w];
+                clamp_words(e);                                // x25519.c:170-172
+                sc_reduce256(x, e);                            // Q9
+            }
             ge_p3 R;
-            ed25519_sign_front(AR[2 * k].v, AR[2 * k + 1].v, R, sec + 32 * i, m, len, s_comb);
-            fe_copy(X[k], R.X); fe_copy(Y[k], R.Y); fe_copy(Z[k], R.Z);
+            ge_scalarmult_base_ct(R, x, s_comb);
+            if (MODE == 0) { fe_copy(U[k], R.X); fe_copy(V[k], R.Y); fe_copy(Z[k], R.Z); }
+            else { fe_add(U[k], R.Z, R.Y); fe_sub(Z[k], R.Z, R.Y); }                       // x25519.c:190-194
             cnt++;
         }
-        if (RAGGED && cnt == 0) continue;                      // (public: no work for this thread in the last round)
         fe_batch_inv(Z, cnt);
 #pragma unroll 1
         for (int k = 0; k < cnt; k++) {
-            const size_t i = op_index(k);
-            u32 p[8], o[16];
-            const uint8_t *m; u64 len;
-            msg_of(m, len, msgs, off, fixed_len, i);
-            load8(p, pub, i);
-            ed25519_sign_back(o, AR[2 * k].v, AR[2 * k + 1].v, X[k], Y[k], Z[k], p, m, len);
-            store8(sig, 2 * i, o);
-            store8(sig, 2 * i + 1, o + 8);
+            u32 o[8];
+            if (MODE == 0) ge_tobytes_zinv(o, U[k], V[k], Z[k]);
+            else x25519_back(o, U[k], Z[k]);
+            uint4 *p = reinterpret_cast<uint4 *>(out + (size_t)out_stride * (i0 + (size_t)k * T));
+            p[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            p[1] = make_uint4(o[4], o[5], o[6], o[7]);
         }
-        scrub(X, EDG_BATCH);
-        scrub(Y, EDG_BATCH);
+        scrub(U, EDG_BATCH);
+        scrub(V, MODE == 0 ? EDG_BATCH : 1);
         scrub(Z, EDG_BATCH);
-        scrub(AR, 2 * EDG_BATCH);
     }
+}
+
+// a[i] = clamp(SHA512(sec[i])[0..31]) mod L                                     [ed25519_key_setup, ed25519-sha512.c:31-47, :62]
+__global__ void __launch_bounds__(kThreads) k_expand_key(size_t n, u32 *a_out, const uint8_t *sec) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 a[8];
+        u64 prefix[4];
+        ed25519_expand_key(a, prefix, sec + 32 * i);
+        store_words8(a_out + 8 * i, a);
+    }
+}
+
+// Visits operations [0, n) once each: one per thread per grid stride, or (RAGGED: the batch has an offsets array) in
+// tiles of kMsgTile consecutive operations sorted by message length in shared memory (kernel_common.cuh), so that
+// neighbouring lanes get messages of neighbouring lengths.  Lengths are public.
+template <bool RAGGED, typename F>
+__device__ __forceinline__ void for_each_message(size_t n, const unsigned long long *off, F body) {
+    if (!RAGGED) {
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) body(i);
+    } else {
+        __shared__ u32 s_key[kMsgTile];
+        for (size_t t0 = (size_t)blockIdx.x * kMsgTile; t0 < n; t0 += (size_t)gridDim.x * kMsgTile) {
+            __syncthreads();                                   // the previous tile's keys are no longer needed
+            for (int e = threadIdx.x; e < kMsgTile; e += blockDim.x) s_key[e] = ragged_key<kMsgTileBits>(off, t0, e, n);
+            block_sort_u32<kMsgTile>(s_key);
+            for (int e = threadIdx.x; e < kMsgTile; e += blockDim.x) {
+                const u32 key = s_key[e];
+                if (key == 0xffffffffu) break;                 // past the end of the batch (sorted last)
+                body(t0 + (key & (kMsgTile - 1)));
+            }
+        }
+    }
+}
+
+// sign, stage 1: a[i] (as k_expand_key) and the nonce r[i] = H(prefix || M) mod L                  [ed25519-sha512.c:96-105]
+template <bool RAGGED>
+__global__ void __launch_bounds__(kThreads) k_sign_nonce(size_t n, u32 *a_out, u32 *r_out, const uint8_t *sec, const uint8_t *msgs,
+                                                         const unsigned long long *off, unsigned long long fixed_len) {
+    for_each_message<RAGGED>(n, off, [&](size_t i) {
+        const uint8_t *m; u64 len;
+        msg_of(m, len, msgs, off, fixed_len, i);
+        u32 a[8], r[8];
+        ed25519_sign_nonce(a, r, sec + 32 * i, m, len);
+        store_words8(a_out + 8 * i, a);
+        store_words8(r_out + 8 * i, r);
+    });
+}
+
+// sign, stage 3: S = r + H(R || pub || M) a mod L next to the R bytes k_comb wrote into sig[i]; wipes a[i], r[i].  [:112-122]
+template <bool RAGGED>
+__global__ void __launch_bounds__(kThreads) k_sign_finish(size_t n, uint8_t *sig, u32 *a_in, u32 *r_in, const uint8_t *pub, const uint8_t *msgs,
+                                                          const unsigned long long *off, unsigned long long fixed_len) {
+    for_each_message<RAGGED>(n, off, [&](size_t i) {
+        const uint8_t *m; u64 len;
+        msg_of(m, len, msgs, off, fixed_len, i);
+        u32 a[8], r[8], R[8], p[8], S[8];
+        load_words8(a, a_in + 8 * i);
+        load_words8(r, r_in + 8 * i);
+        wipe_words8(a_in + 8 * i);
+        wipe_words8(r_in + 8 * i);
+        load8(R, sig, 2 * i);
+        load8(p, pub, i);
+        ed25519_sign_finish(S, a, r, R, p, m, len);
+        store8(sig, 2 * i + 1, S);
+    });
 }
 
 __global__ void __launch_bounds__(kThreads) k_sk_convert(size_t n, uint8_t *out, const uint8_t *in) {
@@ -152,44 +167,86 @@ __global__ void __launch_bounds__(kThreads) k_sk_convert(size_t n, uint8_t *out,
     }
 }
 
+// comb table: bases[j] = 2^(W j) B (one thread per row), then row j = 1 .. 2^(W-1) multiples of bases[j]
+__global__ void k_comb_base(u32 *bases) { wtab_base(bases + 24 * threadIdx.x, EDG_COMB_W * (int)threadIdx.x); }
+
+__global__ void k_comb_rows(u32 *table, const u32 *bases) {
+    const unsigned g = blockIdx.x * blockDim.x + threadIdx.x, row = g / (EDG_COMB_ENTRIES / 8), grp = g % (EDG_COMB_ENTRIES / 8);
+    if (row < EDG_COMB_ROWS) wtab_build8(table + (size_t)row * (EDG_COMB_ENTRIES * 24) + 24u * 8u * grp, bases + 24 * row, 8u * grp + 1u);
+}
+
+template <typename K>
+int msg_grid(K kernel, size_t n, bool ragged, int sm_count) {
+    int bps = 0;
+    grid_for(kernel, n, 0, sm_count, &bps);
+    const size_t per = ragged ? (size_t)kMsgTile : (size_t)kThreads, need = (n + per - 1) / per, cap = (size_t)sm_count * bps;
+    return (int)(need < cap ? need : cap);
+}
+
+int comb_grid(size_t n, int sm_count) {
+    const size_t need = (n + kCombThreads - 1) / kCombThreads, cap = (size_t)sm_count * EDG_COMB_BLOCKS;
+    return (int)(need < cap ? need : cap);
+}
+
 }  // namespace
 
 extern "C" {
 
-int edg_fixedbase_init(void) {
+int edg_kernels_init(void) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(k_x25519_base, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
-    e = cudaFuncSetAttribute(k_genpub, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
-    e = cudaFuncSetAttribute(k_sign<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
-    e = cudaFuncSetAttribute(k_sign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_comb<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
+    e = cudaFuncSetAttribute(k_comb<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCombBytes); if (e) return (int)e;
     return 0;
 }
 
-int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, int sm_count, void *stream) {
-    if (n == 0) return 0;
-    int g = grid_for(k_x25519_base, n, kCombBytes, sm_count, nullptr);
-    k_x25519_base<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, out, scalar);
+size_t edg_comb_table_payload_bytes(void) { return (size_t)EDG_COMB_WORDS * sizeof(u32); }
+size_t edg_comb_table_bytes(void) { return ((size_t)EDG_COMB_WORDS + 24u * EDG_COMB_ROWS) * sizeof(u32); }   // + the row base points
+void edg_comb_geometry(int *rows, int *entries) { *rows = EDG_COMB_ROWS; *entries = EDG_COMB_ENTRIES; }
+
+int edg_comb_table_init(void *table, void *stream) {
+    u32 *t = (u32 *)table, *bases = t + EDG_COMB_WORDS;
+    k_comb_base<<<1, EDG_COMB_ROWS, 0, (cudaStream_t)stream>>>(bases);
+    const unsigned groups = EDG_COMB_ROWS * (EDG_COMB_ENTRIES / 8);
+    k_comb_rows<<<(groups + 63) / 64, 64, 0, (cudaStream_t)stream>>>(t, bases);
     return (int)cudaGetLastError();
 }
 
-int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, int sm_count, void *stream) {
+// scratch of one pass: the secret scalar a (genpub, sign) and the nonce r (sign), 32 bytes each per operation
+size_t edg_fixedbase_scratch_bytes(int is_sign, size_t n) { return (n < kPass ? n : kPass) * (is_sign ? 64 : 32); }
+
+int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, const void *comb, int sm_count, void *stream) {
     if (n == 0) return 0;
-    int g = grid_for(k_genpub, n, kCombBytes, sm_count, nullptr);
-    k_genpub<<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, pub, sec);
+    k_comb<1><<<comb_grid(n, sm_count), kCombThreads, kCombBytes, (cudaStream_t)stream>>>(n, out, 32u, (u32 *)scalar, 0, (const u32 *)comb);
     return (int)cudaGetLastError();
 }
 
-int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs,
-                    const unsigned long long *off, unsigned long long fixed_len, int sm_count, void *stream) {
-    if (n == 0) return 0;
-    if (off) {                                                 // ragged: tiles of kThreads x EDG_BATCH signatures per block
-        int bps = 0;
-        grid_for(k_sign<true>, n, kCombBytes, sm_count, &bps);
-        const size_t tiles = (n + (size_t)kThreads * EDG_BATCH - 1) / ((size_t)kThreads * EDG_BATCH), cap = (size_t)sm_count * bps;
-        k_sign<true><<<(unsigned)(tiles < cap ? tiles : cap), kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
-    } else {
-        int g = grid_for(k_sign<false>, n, kCombBytes, sm_count, nullptr);
-        k_sign<false><<<g, kThreads, kCombBytes, (cudaStream_t)stream>>>(n, sig, sec, pub, msgs, off, fixed_len);
+int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, void *scratch, const void *comb, int sm_count, void *stream, unsigned *launches) {
+    cudaStream_t st = (cudaStream_t)stream;
+    u32 *a = (u32 *)scratch;
+    for (size_t first = 0; first < n; first += kPass) {
+        const size_t m = n - first < kPass ? n - first : kPass;
+        k_expand_key<<<msg_grid(k_expand_key, m, false, sm_count), kThreads, 0, st>>>(m, a, sec + 32 * first);
+        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, pub + 32 * first, 32u, a, 1, (const u32 *)comb);
+        *launches += 2;
+    }
+    return (int)cudaGetLastError();
+}
+
+int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *pub, const uint8_t *msgs, const unsigned long long *off,
+                    unsigned long long fixed_len, void *scratch, const void *comb, int sm_count, void *stream, unsigned *launches) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cap = n < kPass ? n : kPass;
+    u32 *a = (u32 *)scratch, *r = a + 8 * cap;
+    for (size_t first = 0; first < n; first += kPass) {
+        const size_t m = n - first < kPass ? n - first : kPass;
+        const uint8_t *mp = off ? msgs : msgs + first * fixed_len;
+        const unsigned long long *op = off ? off + first : nullptr;
+        if (off) k_sign_nonce<true><<<msg_grid(k_sign_nonce<true>, m, true, sm_count), kThreads, 0, st>>>(m, a, r, sec + 32 * first, mp, op, fixed_len);
+        else k_sign_nonce<false><<<msg_grid(k_sign_nonce<false>, m, false, sm_count), kThreads, 0, st>>>(m, a, r, sec + 32 * first, mp, op, fixed_len);
+        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, sig + 64 * first, 64u, r, 0, (const u32 *)comb);
+        if (off) k_sign_finish<true><<<msg_grid(k_sign_finish<true>, m, true, sm_count), kThreads, 0, st>>>(m, sig + 64 * first, a, r, pub + 32 * first, mp, op, fixed_len);
+        else k_sign_finish<false><<<msg_grid(k_sign_finish<false>, m, false, sm_count), kThreads, 0, st>>>(m, sig + 64 * first, a, r, pub + 32 * first, mp, op, fixed_len);
+        *launches += 3;
     }
     return (int)cudaGetLastError();
 }

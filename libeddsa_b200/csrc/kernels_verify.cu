@@ -1,7 +1,12 @@
-// Verification kernels (sm_100a), one signature per thread, in two stages (ops.cuh: ed25519_verify_front / _loop):
-//   k_verify_front  SHA-512 challenge, half-gcd (hgcd.cuh), decompression of A and R, the two 8-entry tables
+// Verification kernels (sm_100a), one signature per thread, in stages (ops.cuh: ed25519_verify_front_* / _loop):
+//   front, scalars  SHA-512 challenge, half-gcd (hgcd.cuh), |rho| S mod L              — ALU work, no field arithmetic
+//   front, points   decompression of A and R, the two 8-entry tables                   — field arithmetic only
 //   k_verify        Straus multi-scalar multiplication over ~33 signed 4-bit windows (uniform control flow) and the
 //                   projective comparison with the neutral element
+// The two front halves are independent.  Fixed-length batches run them in ONE launch, k_verify_front, whose blocks
+// alternate between the two roles, so every SM holds blocks of both kinds and the ALU-bound half hides under the
+// multiplier-bound one; ragged batches (an offsets array) run the scalars half as its own kernel over tiles sorted by
+// message length (k_verify_scalars<true>), followed by the points half.
 // Public data only, so table lookups are direct-indexed.
 // Also hosts pk_ed25519_to_x25519 (it shares the decompression).
 // Replaces ed25519_verify / pk_ed25519_to_x25519: /root/reference/lib/ed25519-sha512.c:148-237.
@@ -10,10 +15,10 @@
 using namespace edg;
 
 #ifndef EDG_VERIFY_WAVES
-#define EDG_VERIFY_WAVES 4  /* waves of resident threads per pass: sizes the per-signature records in scratch */
+#define EDG_VERIFY_WAVES 4  /* waves of resident threads per pass (default; EDDSA_B200_VERIFY_WAVES overrides): sizes the records */
 #endif
 #ifndef EDG_LB_VERIFY
-#define EDG_LB_VERIFY 4     /* front kernel: min resident blocks per SM the register allocator must allow: 128 registers, 4 warps
+#define EDG_LB_VERIFY 4     /* front kernels: min resident blocks per SM the register allocator must allow: 128 registers, 4 warps
                                per scheduler */
 #endif
 #ifndef EDG_VTHREADS
@@ -23,53 +28,98 @@ using namespace edg;
 #ifndef EDG_LB_VLOOP
 #define EDG_LB_VLOOP EDG_LB_VERIFY
 #endif
+#ifndef EDG_VFRONT_FUSED
+#define EDG_VFRONT_FUSED 1  /* fixed-length batches: both front halves in one launch, roles alternating by block */
+#endif
+#ifndef EDG_MSG_TILE
+#define EDG_MSG_TILE 2048   /* ragged batches: consecutive signatures sorted by message length together */
+#endif
 namespace {
 constexpr int kVThreads = EDG_VTHREADS;
+constexpr int kMsgTile = EDG_MSG_TILE;
+constexpr int kMsgTileBits = kMsgTile == 512 ? 9 : kMsgTile == 1024 ? 10 : kMsgTile == 2048 ? 11 : 12;
+static_assert(kMsgTile == (1 << kMsgTileBits), "tile size must be a power of two between 512 and 4096");
 
-// stage 1: one signature per thread -> one EDG_VSTATE_WORDS-word record.  Records are handed out sorted by window
-// count: signatures needing more than EDG_NWIN_SPLIT windows (5 %) fill the record array from the front, the others
-// from the back, so a warp of the loop kernel (which runs the maximum over its lanes) almost never waits for a
-// single long lane: 33.9 -> 33.05 windows on average.  Slots come from two counters (one warp-aggregated atomic each).
+// Records are visited by the loop kernel through perm[], sorted by window count: signatures needing more than
+// EDG_NWIN_SPLIT windows (5 %) take positions from the front, the others from the back, so a warp of the loop kernel
+// (which runs the maximum over its lanes) almost never waits for a single long lane: 33.9 -> 33.05 windows on average,
+// and the few long warps start first.  Positions come from two counters, one warp-aggregated atomic each.
 #define EDG_NWIN_SPLIT 33
-__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t n, size_t first, const uint8_t *sig, const uint8_t *pub,
-                                                     const uint8_t *msgs, const unsigned long long *off, unsigned long long fixed_len,
-                                                     u32 *state, unsigned int *counters, int full_scalars) {
-    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((k & ~(size_t)31) >= n) return;                    // whole warps stay (full-mask votes below)
-    const bool live = k < n;
-    const size_t i = first + (live ? k : n - 1);
+
+// scalars half for signature k of the pass (record k); callable from diverged code (lanes group by __activemask)
+__device__ __forceinline__ void verify_scalars_of(size_t n, size_t k, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
+                                                  const unsigned long long *off, unsigned long long fixed_len, u32 *state,
+                                                  unsigned int *perm, unsigned int *counters, int full_scalars) {
     const uint8_t *m; u64 len;
-    msg_of(m, len, msgs, off, fixed_len, i);
-    const u32 *sg = reinterpret_cast<const u32 *>(sig + 64 * i), *pk = reinterpret_cast<const u32 *>(pub + 32 * i);
+    msg_of(m, len, msgs, off, fixed_len, k);
+    const u32 *sg = reinterpret_cast<const u32 *>(sig + 64 * k), *pk = reinterpret_cast<const u32 *>(pub + 32 * k);
     verify_scalars v;
     const int nwin = ed25519_verify_front_scalars(v, sg, pk, m, len, full_scalars != 0);
-    __syncwarp();
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lo = __ballot_sync(0xffffffffu, live && nwin <= EDG_NWIN_SPLIT);
-    const unsigned hi = __ballot_sync(0xffffffffu, live && nwin > EDG_NWIN_SPLIT);
+    ed25519_verify_store_scalars(state + k * EDG_VSTATE_WORDS, v, nwin);
+    const unsigned active = __activemask();
+    const unsigned lane = threadIdx.x & 31u, leader = __ffs(active) - 1;
+    const unsigned lo = __ballot_sync(active, nwin <= EDG_NWIN_SPLIT), hi = active & ~lo;
     unsigned base_lo = 0, base_hi = 0;
-    if (lane == 0) {
+    if (lane == leader) {
         if (lo) base_lo = atomicAdd(&counters[0], (unsigned)__popc(lo));
         if (hi) base_hi = atomicAdd(&counters[1], (unsigned)__popc(hi));
     }
-    base_lo = __shfl_sync(0xffffffffu, base_lo, 0);
-    base_hi = __shfl_sync(0xffffffffu, base_hi, 0);
-    if (!live) return;
+    base_lo = __shfl_sync(active, base_lo, leader);
+    base_hi = __shfl_sync(active, base_hi, leader);
     const unsigned below = (1u << lane) - 1u;
-    // the few long ones go to the FRONT of the array (their warps start first, the kernel's tail is made of short ones)
-    const size_t slot = nwin <= EDG_NWIN_SPLIT ? n - 1 - ((size_t)base_lo + __popc(lo & below)) : (size_t)base_hi + __popc(hi & below);
-    ed25519_verify_front_points(state + slot * EDG_VSTATE_WORDS, v, nwin, (u32)k, sg, pk);
+    const size_t pos = nwin <= EDG_NWIN_SPLIT ? n - 1 - ((size_t)base_lo + __popc(lo & below)) : (size_t)base_hi + __popc(hi & below);
+    perm[pos] = (unsigned)k;
 }
 
-// stage 2: the window loop.  Whole warps stay together (the trip count is agreed per warp with a full-mask
-// reduction): lanes past the end redo the last record and drop the result.
-__global__ void __launch_bounds__(kVThreads, EDG_LB_VLOOP) k_verify(size_t n, uint8_t *ok, const u32 *state, const u32 *__restrict__ wtab) {
+// front, both halves in one launch: even blocks run the scalars half, odd blocks the points half of signatures
+// [128 b, 128 b + 128), b = blockIdx.x / 2.
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_front(size_t n, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
+                                                     unsigned long long fixed_len, u32 *state, unsigned int *perm, unsigned int *counters,
+                                                     int full_scalars) {
+    const size_t k = (size_t)(blockIdx.x >> 1) * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if ((blockIdx.x & 1) == 0) verify_scalars_of(n, k, sig, pub, msgs, nullptr, fixed_len, state, perm, counters, full_scalars);
+    else ed25519_verify_front_points(state + k * EDG_VSTATE_WORDS, reinterpret_cast<const u32 *>(sig + 64 * k), reinterpret_cast<const u32 *>(pub + 32 * k));
+}
+
+// the halves as kernels of their own (ragged batches; RAGGED = tiles sorted by message length)
+template <bool RAGGED>
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_scalars(size_t n, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
+                                                       const unsigned long long *off, unsigned long long fixed_len, u32 *state,
+                                                       unsigned int *perm, unsigned int *counters, int full_scalars) {
+    if constexpr (!RAGGED) {
+        const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (k < n) verify_scalars_of(n, k, sig, pub, msgs, off, fixed_len, state, perm, counters, full_scalars);
+    } else {
+        __shared__ u32 s_key[kMsgTile];
+        for (size_t t0 = (size_t)blockIdx.x * kMsgTile; t0 < n; t0 += (size_t)gridDim.x * kMsgTile) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < kMsgTile; e += blockDim.x) s_key[e] = ragged_key<kMsgTileBits>(off, t0, e, n);
+            block_sort_u32<kMsgTile>(s_key);
+            for (int e = threadIdx.x; e < kMsgTile; e += blockDim.x) {
+                const u32 key = s_key[e];
+                if (key == 0xffffffffu) break;
+                verify_scalars_of(n, t0 + (key & (kMsgTile - 1)), sig, pub, msgs, off, fixed_len, state, perm, counters, full_scalars);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, EDG_LB_VERIFY) k_verify_points(size_t n, const uint8_t *sig, const uint8_t *pub, u32 *state) {
     const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if ((k & ~(size_t)31) >= n) return;
-    const u32 *rec = state + (k < n ? k : n - 1) * EDG_VSTATE_WORDS;
+    if (k < n) ed25519_verify_front_points(state + k * EDG_VSTATE_WORDS, reinterpret_cast<const u32 *>(sig + 64 * k), reinterpret_cast<const u32 *>(pub + 32 * k));
+}
+
+// the window loop.  Whole warps stay together (the trip count is agreed per warp with a full-mask reduction): lanes
+// past the end redo the last record and drop the result.
+__global__ void __launch_bounds__(kVThreads, EDG_LB_VLOOP) k_verify(size_t n, uint8_t *ok, const u32 *state, const unsigned int *perm,
+                                                                   const u32 *__restrict__ wtab) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((j & ~(size_t)31) >= n) return;
+    const unsigned k = perm[j < n ? j : n - 1];
     __shared__ uint4 s_stage[16 * kVThreads];                  // 2 table entries x 8 x 16 bytes per thread, chunk-major
-    const u32 r = ed25519_verify_loop(rec, wtab, reinterpret_cast<u32 *>(s_stage));
-    if (k < n) ok[rec[602]] = (uint8_t)r;
+    const u32 r = ed25519_verify_loop(state + (size_t)k * EDG_VSTATE_WORDS, wtab, reinterpret_cast<u32 *>(s_stage));
+    if (j < n) ok[k] = (uint8_t)r;
 }
 
 // Window tables of B and 2^128 B (built once per device): entry e = e * P, e = 0 .. 2^15.
@@ -94,22 +144,29 @@ __global__ void __launch_bounds__(kThreads) k_pk_convert(size_t n, uint8_t *out,
     }
 }
 
+int g_waves = EDG_VERIFY_WAVES;
+int g_full_scalars = 0;
+
 }  // namespace
 
 extern "C" {
 
-// signatures per pass: a whole number of waves of the loop kernel (resident threads of the device)
-static size_t verify_chunk(int sm_count) {
+// signatures per full pass: a whole number of waves of the loop kernel (resident threads of the device)
+size_t edg_verify_pass(int sm_count) {
     int bps = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_verify, kVThreads, 0) != cudaSuccess || bps < 1) bps = 1;
-    return (size_t)sm_count * bps * kVThreads * EDG_VERIFY_WAVES;
+    return (size_t)sm_count * bps * kVThreads * g_waves;
 }
 
+void edg_verify_set_waves(int waves) { g_waves = waves < 1 ? 1 : waves > 16 ? 16 : waves; }
+unsigned edg_verify_waves(void) { return (unsigned)g_waves; }
 size_t edg_verify_record_bytes(void) { return EDG_VSTATE_WORDS * sizeof(u32); }
-unsigned edg_verify_waves(void) { return EDG_VERIFY_WAVES; }
 
-// the record slab of one pass; its last 256 bytes hold the slot counters of the passes (two per pass, zeroed by the launcher)
-size_t edg_verify_scratch_bytes(int sm_count) { return verify_chunk(sm_count) * EDG_VSTATE_WORDS * sizeof(u32) + 256; }
+// scratch of a pass of up to `records` signatures: the records, the permutation the loop kernel visits them in, and
+// 256 bytes of position counters
+static size_t perm_offset(size_t records) { return records * EDG_VSTATE_WORDS * sizeof(u32); }
+static size_t counters_offset(size_t records) { return perm_offset(records) + ((records * sizeof(unsigned) + 255) & ~(size_t)255); }
+size_t edg_verify_scratch_bytes(size_t records) { return counters_offset(records) + 256; }
 
 size_t edg_verify_table_bytes(void) { return (2 * (size_t)EDG_WTAB_WORDS + 48) * sizeof(u32); }
 
@@ -124,25 +181,38 @@ int edg_verify_table_init(void *table, void *stream) {
 }
 
 // test hook (EDDSA_B200_DEBUG_FULL_SCALARS=1): every signature takes the full-length fallback (rho, tau) = (1, t)
-static int g_full_scalars = 0;
 void edg_verify_debug_full_scalars(int on) { g_full_scalars = on; }
 
-// kernels edg_launch_verify(n, ..) launches: two per pass
-unsigned edg_verify_launches(size_t n, int sm_count) {
-    const size_t chunk = verify_chunk(sm_count);
-    return (unsigned)(2 * ((n + chunk - 1) / chunk));
-}
-
+// scratch: edg_verify_scratch_bytes(records) bytes; a pass handles up to `records` signatures
 int edg_launch_verify(size_t n, uint8_t *ok, const uint8_t *sig, const uint8_t *pub, const uint8_t *msgs,
-                      const unsigned long long *off, unsigned long long fixed_len, void *scratch, const void *table,
-                      int sm_count, void *stream) {
-    const size_t chunk = verify_chunk(sm_count);
-    unsigned int *counters = (unsigned int *)((u32 *)scratch + chunk * EDG_VSTATE_WORDS);
-    for (size_t first = 0; first < n; first += chunk) {
-        const size_t m = n - first < chunk ? n - first : chunk;
-        cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), (cudaStream_t)stream);
-        k_verify_front<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(m, first, sig, pub, msgs, off, fixed_len, (u32 *)scratch, counters, g_full_scalars);
-        k_verify<<<(unsigned)((m + kVThreads - 1) / kVThreads), kVThreads, 0, (cudaStream_t)stream>>>(m, ok + first, (const u32 *)scratch, (const u32 *)table);
+                      const unsigned long long *off, unsigned long long fixed_len, void *scratch, size_t records, const void *table,
+                      int sm_count, void *stream, unsigned *launches) {
+    cudaStream_t st = (cudaStream_t)stream;
+    u32 *state = (u32 *)scratch;
+    unsigned int *perm = (unsigned int *)((uint8_t *)scratch + perm_offset(records));
+    unsigned int *counters = (unsigned int *)((uint8_t *)scratch + counters_offset(records));
+    if (records == 0) return (int)cudaErrorInvalidValue;
+    for (size_t first = 0; first < n; first += records) {
+        const size_t m = n - first < records ? n - first : records;
+        const unsigned nb = (unsigned)((m + kThreads - 1) / kThreads);
+        const uint8_t *sg = sig + 64 * first, *pk = pub + 32 * first;
+        cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st);
+        if (off) {
+            int bps = 0;
+            grid_for(k_verify_scalars<true>, m, 0, sm_count, &bps);
+            const size_t tiles = (m + kMsgTile - 1) / kMsgTile, cap = (size_t)sm_count * bps;
+            k_verify_scalars<true><<<(unsigned)(tiles < cap ? tiles : cap), kThreads, 0, st>>>(m, sg, pk, msgs, off + first, fixed_len, state, perm, counters, g_full_scalars);
+            k_verify_points<<<nb, kThreads, 0, st>>>(m, sg, pk, state);
+            *launches += 3;
+        } else if (EDG_VFRONT_FUSED) {
+            k_verify_front<<<2 * nb, kThreads, 0, st>>>(m, sg, pk, msgs + first * fixed_len, fixed_len, state, perm, counters, g_full_scalars);
+            *launches += 2;
+        } else {
+            k_verify_scalars<false><<<nb, kThreads, 0, st>>>(m, sg, pk, msgs + first * fixed_len, nullptr, fixed_len, state, perm, counters, g_full_scalars);
+            k_verify_points<<<nb, kThreads, 0, st>>>(m, sg, pk, state);
+            *launches += 3;
+        }
+        k_verify<<<(unsigned)((m + kVThreads - 1) / kVThreads), kVThreads, 0, st>>>(m, ok + first, state, perm, (const u32 *)table);
     }
     return (int)cudaGetLastError();
 }

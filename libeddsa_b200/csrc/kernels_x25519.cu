@@ -36,9 +36,20 @@ __global__ void __launch_bounds__(kThreads, EDG_LB_X25519) k_x25519(size_t n, ui
     }
 }
 
-// Diagnostic kernel: one field operation per thread on raw 256-bit operands (weakly reduced inputs are
-// legal), so the PTX carry-chain arithmetic of fe.cuh can be checked on the GPU against big integers.
+// Diagnostic kernels: one field / scalar operation per thread on raw operands (weakly reduced field inputs are legal), so
+// the PTX carry-chain arithmetic of fe.cuh and the Barrett code of sc.cuh can be checked on the GPU against big integers.
 __global__ void __launch_bounds__(kThreads) k_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, int op) {
+    if (op == 9) {                                             // shared inversion of each group of EDG_BATCH consecutive items
+        const size_t groups = (n + EDG_BATCH - 1) / EDG_BATCH;
+        for (size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (size_t)gridDim.x * blockDim.x) {
+            fe z[EDG_BATCH];
+            const int cnt = (int)(n - g * EDG_BATCH < EDG_BATCH ? n - g * EDG_BATCH : EDG_BATCH);
+            for (int k = 0; k < cnt; k++) load8(z[k].v, a, g * EDG_BATCH + k);
+            fe_batch_inv(z, cnt);
+            for (int k = 0; k < cnt; k++) { u32 w[8]; fe_to_words(w, z[k]); store8(out, g * EDG_BATCH + k, w); }
+        }
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         fe x, y, r;
         load8(x.v, a, i);
@@ -59,6 +70,20 @@ __global__ void __launch_bounds__(kThreads) k_fe_selftest(size_t n, uint8_t *out
     }
 }
 
+// op 0: out = (a + 2^256 b) mod L (sc_reduce512); 1: out = a mod L (sc_reduce256); 2: out = a b + c mod L (sc_muladd)
+__global__ void __launch_bounds__(kThreads) k_sc_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, const uint8_t *c, int op) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        u32 x[16], z[8], r[8];
+        load8(x, a, i);
+        load8(x + 8, b, i);
+        load8(z, c, i);
+        if (op == 0) sc_reduce512(r, x);
+        else if (op == 1) sc_reduce256(r, x);
+        else sc_muladd(r, x, x + 8, z);
+        store8(out, i, r);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -70,6 +95,13 @@ int edg_launch_fe_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8
     return (int)cudaGetLastError();
 }
 
+
+int edg_launch_sc_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8_t *b, const uint8_t *c, int op, int sm_count, void *stream) {
+    if (n == 0) return 0;
+    int g = grid_for(k_sc_selftest, n, 0, sm_count, nullptr);
+    k_sc_selftest<<<g, kThreads, 0, (cudaStream_t)stream>>>(n, out, a, b, c, op);
+    return (int)cudaGetLastError();
+}
 
 int edg_launch_x25519(size_t n, uint8_t *out, const uint8_t *scalar, const uint8_t *point, int sm_count, void *stream) {
     if (n == 0) return 0;

@@ -133,23 +133,24 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fixed-base scalar multiplication r = x * B for SECRET x in [0, L): signed radix-16 comb, one
-// table row per digit (no doublings), constant-time masked row scan.     [ed_scale_base, ed.c:397-430]
-// comb = BASE_COMB (64 rows x 8 entries x 24 words = 49 152 bytes), staged in shared memory.
+// Fixed-base scalar multiplication r = x * B for SECRET x in [0, L): signed radix-2^W comb (sc.cuh: EDG_COMB_W), one
+// table row per digit (no doublings), constant-time masked row scan.                 [ed_scale_base, ed.c:397-430]
+// comb = EDG_COMB_ROWS rows x EDG_COMB_ENTRIES entries x 24 words: entry [j][k] = (k + 1) * 2^(W j) * B in affine
+// precomputed form, built once per device (comb_table_row below) and staged in shared memory by the kernels.
 // ------------------------------------------------------------------------------------------------
 EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
     u32 e[8];
-    sc_recode_radix16(e, x);
+    sc_recode_comb(e, x);
     ge_identity(r);
 #pragma unroll 1
-    for (int j = 0; j < 64; j++) {
-        const int digit = (int)(e[0] & 15u) - 8;
+    for (int j = 0; j < EDG_COMB_ROWS; j++) {
+        const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
 #pragma unroll
-        for (int i = 0; i < 7; i++) e[i] = (e[i] >> 4) | (e[i + 1] << 28);
-        e[7] >>= 4;
+        for (int i = 0; i < 7; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
+        e[7] >>= EDG_COMB_W;
         ge_pre t;
-        ge_pre_select_ct(t, comb + j * 192, digit);
-        ge_madd(r, r, t, true);
+        ge_pre_select_ct<EDG_COMB_ENTRIES>(t, comb + j * (EDG_COMB_ENTRIES * 24), digit);
+        ge_madd(r, r, t, j + 1 < EDG_COMB_ROWS);              // (public loop position) the last addition needs no T
     }
 }
 
@@ -197,40 +198,42 @@ EDG_HD void ed25519_genpub_op(u32 pub[8], const uint8_t *sk, const u32 *comb) {
 }
 
 // sig = (R, S)                                                        [sign, ed25519-sha512.c:84-123]
-// front: secret scalar a, nonce r = H(prefix || M) mod L and the point R = r B (projective)
-EDG_HD void ed25519_sign_front(u32 a[8], u32 r[8], ge_p3 &R, const uint8_t *sk, const uint8_t *msg, u64 len, const u32 *comb) {
+// Three stages, each its own kernel (kernels_fixedbase.cu), so that the comb runs in a small multiplier-bound
+// kernel and the hashing in small ALU-bound ones:
+//   nonce : secret scalar a and nonce r = H(prefix || M) mod L                                    :96-105
+//   comb  : R = r B, encoded (shared with genpub / x25519_base)                                    :108-110
+//   finish: t = H(R || pub || M) mod L with pub as given (Q8), S = r + t a mod L                   :112-122
+EDG_HD void ed25519_sign_nonce(u32 a[8], u32 r[8], const uint8_t *sk, const uint8_t *msg, u64 len) {
     u32 h[16];
     u64 pre[4], st[8];
     ed25519_expand_key(a, pre, sk);
-    sha512_prefixed<4>(st, pre, msg, len);                // r = H(prefix || M)        :101-105
+    sha512_prefixed<4>(st, pre, msg, len);
     sha512_state_to_le_words(h, st);
     sc_reduce512(r, h);
-    ge_scalarmult_base_ct(R, r, comb);                    // R = r B                   :108-109
 }
 
-// back: encode R, t = H(R || pub || M) mod L with pub as given (Q8), S = r + t a mod L
-EDG_HD void ed25519_sign_back(u32 sig[16], const u32 a[8], const u32 r[8], const fe &X, const fe &Y, const fe &zinv,
-                              const u32 pub[8], const uint8_t *msg, u64 len) {
+EDG_HD void ed25519_sign_finish(u32 S[8], const u32 a[8], const u32 r[8], const u32 Renc[8], const u32 pub[8], const uint8_t *msg, u64 len) {
     u32 t[8], h[16];
     u64 pre[8], st[8];
-    ge_tobytes_zinv(sig, X, Y, zinv);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {                          // :112-117
-        pre[k] = be64_from_le_words(sig[2 * k], sig[2 * k + 1]);
+    for (int k = 0; k < 4; k++) {
+        pre[k] = be64_from_le_words(Renc[2 * k], Renc[2 * k + 1]);
         pre[4 + k] = be64_from_le_words(pub[2 * k], pub[2 * k + 1]);
     }
     sha512_prefixed<8>(st, pre, msg, len);
     sha512_state_to_le_words(h, st);
     sc_reduce512(t, h);
-    sc_muladd(sig + 8, t, a, r);                          // S = r + t a mod L         :120-122
+    sc_muladd(S, t, a, r);
 }
 
 EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], const uint8_t *msg, u64 len, const u32 *comb) {
     u32 a[8], r[8];
     ge_p3 R;
-    ed25519_sign_front(a, r, R, sk, msg, len, comb);
+    ed25519_sign_nonce(a, r, sk, msg, len);
+    ge_scalarmult_base_ct(R, r, comb);
     fe_inv(R.Z, R.Z);
-    ed25519_sign_back(sig, a, r, R.X, R.Y, R.Z, pub, msg, len);
+    ge_tobytes_zinv(sig, R.X, R.Y, R.Z);
+    ed25519_sign_finish(sig + 8, a, r, sig, pub, msg, len);
 }
 
 // out = u-coordinate of (clamp(scalar) mod L) * B                     [do_x25519_base, x25519.c:158-197]
@@ -346,6 +349,13 @@ EDG_HD void wtab_build8(u32 *out, const u32 *base, u32 e0) {
     }
 }
 
+// Row j of the comb table: entries (k + 1) * 2^(W j) * B, k = 0 .. EDG_COMB_ENTRIES - 1 (24 words each), from the
+// row's base point in affine precomputed form (wtab_base(base, W j)).
+EDG_HD void comb_table_row(u32 *row, const u32 *base) {
+#pragma unroll 1
+    for (u32 g = 0; g < EDG_COMB_ENTRIES / 8; g++) wtab_build8(row + 24u * 8u * g, base, 8u * g + 1u);
+}
+
 // entry |digit| of a window table in global memory, negated when digit < 0 (public data: direct index)
 EDG_HD void ge_pre_load_wtab(ge_pre &t, const u32 *tbl, int digit) {
     const u32 neg = (u32)(digit >> 31);
@@ -398,24 +408,26 @@ EDG_HD int sc_digit16(const u32 *e, int j) { return (int)((e[j >> 3] >> (4 * (j 
 
 // sig / pub point at this signature's 64 / 32 bytes (16-byte aligned).
 // Accept iff  encode(S*B - t*A) == sig[0..31]  and A decodes to a curve point (Q2, Q5 policy), decided as
-//   sig[0..31] canonical encoding of a curve point R'   and   (rho S)*B + tau*(-+A) + |rho|*(-R') == O
+//   sig[0..31] canonical encoding of a curve point R'   and   (|rho| S)*B + (+-tau)*(-A) + |rho|*(-R') == O
 // with the half-size (rho, tau) of hgcd.cuh.  Straus over 4-bit signed windows of tau and |rho| (tables of the
 // two variable points) and 16-bit signed windows of rho S (tables of B and 2^128 B, wtab: 2 x EDG_WTAB_WORDS
 // words, L2-resident), uniform control flow across the warp.
 //
 // Two stages with an EDG_VSTATE_WORDS-word record per signature in between, so that each can be its own kernel
 // (one kernel holding both overflowed the instruction cache: warps in the front part kept evicting the loop):
-//   front: challenge hash, half-gcd, |rho| S mod L, both decompressions, both tables
+//   front: challenge hash, half-gcd, |rho| S mod L (scalars: ALU work only) | both decompressions, both tables (points:
+//          field arithmetic only) — two independent halves, run side by side by the kernels
 //   loop : the window loop and the projective comparison with the neutral element
-// record: [0, 288) table of Q = -sign(rho) A, [288, 576) table of P = -R' (9 cached points x 32 words each),
+// record: [0, 288) table of Q = -A, [288, 576) table of P = -R' (9 cached points x 32 words each),
 //         [576, 584) tau, [584, 592) |rho|, [592, 600) rho S recoded to signed 16-bit digits, [600] flags
-//         (bit 0: both points decoded and the R bytes are canonical), [601] windows needed, [602] index of the
-//         signature within its pass (records are not stored in input order).
+//         (bit 0: both points decoded and the R bytes are canonical), [601] windows needed, [602] sign of rho
+//         (all-ones: the digits of tau are negated in the loop, i.e. Q stands for +A).
+// The scalar words [576, 600) + [601, 603) and the point words [0, 576) + [600] are written by two independent
+// stages (neither reads what the other writes), so they can run side by side; record k belongs to signature k of
+// the pass, and the loop kernel visits the records through a permutation sorted by window count.
 #define EDG_VSTATE_WORDS 608
 
-// front, part 1: the three scalars.  Returns the number of windows this signature needs; the caller then picks the
-// record (kernels: records are handed out sorted by window count, so that the lanes of a warp of the loop kernel
-// agree on their trip count) and calls part 2.
+// front, scalars: returns the number of windows this signature needs.
 struct verify_scalars { u32 et[8], er[8], es[8], rho_neg; };
 
 EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, bool full_scalars = false) {
@@ -444,29 +456,33 @@ EDG_HD int ed25519_verify_front_scalars(verify_scalars &v, const u32 *sig, const
     return nwin < 32 ? 32 : nwin;                         // all 16-bit windows of rho S sit below bit 128
 }
 
-// front, part 2: fill the record — scalars, the tables of Q = -sign(rho) A and P = -R', flags.   :151, :174-175
-EDG_HD void ed25519_verify_front_points(u32 *state, const verify_scalars &v, int nwin, u32 index, const u32 *sig, const u32 *pub) {
+EDG_HD void ed25519_verify_store_scalars(u32 *state, const verify_scalars &v, int nwin) {
 #pragma unroll
     for (int i = 0; i < 8; i++) { state[576 + i] = v.et[i]; state[584 + i] = v.er[i]; state[592 + i] = v.es[i]; }
+    state[601] = (u32)nwin;
+    state[602] = v.rho_neg ? 0xffffffffu : 0u;
+}
+
+// front, points: the tables of Q = -A and P = -R', flags.                                          :151, :174-175
+EDG_HD void ed25519_verify_front_points(u32 *state, const u32 *sig, const u32 *pub) {
     u32 good = 0xffffffffu;
 #pragma unroll 1
     for (int which = 0; which < 2; which++) {             // one loop body for both points: half the code
         ge_p3 Q;
         u32 a[8], canon;
         load_words8(a, which ? sig : pub);
-        good &= ge_frombytes(Q, a, which ? true : (v.rho_neg == 0), &canon);
+        good &= ge_frombytes(Q, a, true, &canon);
         good &= which ? canon : 0xffffffffu;              // only R has to be canonical (Q2); any encoding of A is accepted (Q3)
         ge_cached_table(state + 288 * which, Q);
     }
     state[600] = good & 1u;
-    state[601] = (u32)nwin;
-    state[602] = index;
 }
 
 EDG_HD void ed25519_verify_front(u32 *state, const u32 *sig, const u32 *pub, const uint8_t *msg, u64 len, bool full_scalars = false) {
     verify_scalars v;
     const int nwin = ed25519_verify_front_scalars(v, sig, pub, msg, len, full_scalars);
-    ed25519_verify_front_points(state, v, nwin, 0, sig, pub);
+    ed25519_verify_store_scalars(state, v, nwin);
+    ed25519_verify_front_points(state, sig, pub);
 }
 
 // stage (device only, may be null): this block's shared-memory staging area, 16 chunks x blockDim.x threads x 16 bytes.
@@ -478,6 +494,7 @@ EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab, u32 *stage = 0
 #pragma unroll
     for (int i = 0; i < 8; i++) { et[i] = state[576 + i]; er[i] = state[584 + i]; es[i] = state[592 + i]; }
     const u32 good = state[600];
+    const u32 rho_neg = state[602];                       // all-ones: tau multiplies +A, i.e. its digits change sign
     int nwin = (int)state[601];
 #if defined(__CUDA_ARCH__)
     nwin = __reduce_max_sync(0xffffffffu, nwin);          // one trip count per warp (callers keep all 32 lanes here)
@@ -532,8 +549,9 @@ EDG_HD u32 ed25519_verify_loop(const u32 *state, const u32 *wtab, u32 *stage = 0
                 fe ypx, ymx, t2d, a, b, c, d;
                 if (step < 6) {                               // digit * Q or digit * P: cached entry from this thread's scratch
                     const int dg = sc_digit16(step == 4 ? et : er, j);
-                    const u32 neg = (u32)(dg >> 31);
-                    const u32 absd = ((u32)dg ^ neg) - neg;
+                    const u32 sgn = (u32)(dg >> 31);
+                    const u32 absd = ((u32)dg ^ sgn) - sgn;
+                    const u32 neg = step == 4 ? sgn ^ rho_neg : sgn;
                     ge_cached q;
 #if defined(__CUDA_ARCH__)
                     if (stage) {

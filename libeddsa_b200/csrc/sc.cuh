@@ -107,14 +107,34 @@ EDG_HD void sc_muladd(u32 r[8], const u32 a[8], const u32 b[8], const u32 c[8]) 
     sc_reduce512(r, w);
 }
 
-// Signed radix-16 digits of x in [0, L): e = x + 0x888...8 (no overflow since x < 2^253), nibble_j(e) - 8
-// in [-8, 7] and sum (nibble_j - 8) 16^j = x.  The 64 nibbles are returned packed (8 per word); callers
-// take (e[j>>3] >> 4*(j&7)) & 15 and subtract 8.        [reference: con_off trick, sc.c:40 + ed.c:406-422]
-EDG_HD void sc_recode_radix16(u32 e[8], const u32 x[8]) {
+// Fixed-base comb geometry: signed radix-2^W digits, one table row per digit (no doublings), 2^(W-1) entries per row.
+//   W = 4: 64 rows x  8 entries = 49 152 bytes     W = 5: 51 rows x 16 entries = 78 336 bytes (20 % fewer additions)
+#ifndef EDG_COMB_W
+#define EDG_COMB_W 5
+#endif
+#define EDG_COMB_ROWS ((255 + EDG_COMB_W - 1) / EDG_COMB_W)
+#define EDG_COMB_ENTRIES (1 << (EDG_COMB_W - 1))
+#define EDG_COMB_WORDS (EDG_COMB_ROWS * EDG_COMB_ENTRIES * 24)
+
+// word i of the recoding offset  2^(W-1) * sum_{j < ROWS} 2^(W j)
+EDG_HD constexpr u32 sc_comb_offset_word(int i) {
+    u32 w = 0;
+    for (int j = 0; j < EDG_COMB_ROWS; j++) {
+        const int bit = EDG_COMB_W * j + EDG_COMB_W - 1;
+        if ((bit >> 5) == i) w |= 1u << (bit & 31);
+    }
+    return w;
+}
+
+// Signed radix-2^W digits of x in [0, L): e = x + offset (no overflow: x < 2^253 and offset < 2^255 (W = 5) or
+// < 0.54 * 2^256 (W = 4)), then digit_j = ((e >> W j) mod 2^W) - 2^(W-1) in [-2^(W-1), 2^(W-1)) and
+// sum digit_j 2^(W j) = x.  Returned packed; callers shift W bits out per step.
+//                                                      [reference: con_off trick, sc.c:40 + ed.c:406-422]
+EDG_HD void sc_recode_comb(u32 e[8], const u32 x[8]) {
     u32 carry = 0;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        u64 t = (u64)x[i] + 0x88888888u + carry;
+        const u64 t = (u64)x[i] + sc_comb_offset_word(i) + carry;
         e[i] = (u32)t;
         carry = (u32)(t >> 32);
     }

@@ -12,6 +12,7 @@ for p in (ROOT, HERE):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+    config.addinivalue_line("markers", "slow: full-size configuration (tens of seconds on a B200; part of `-m gpu`)")
 
 
 @pytest.fixture(scope="session")

@@ -105,3 +105,19 @@ def sign_with(a, prefix, A_bytes, msg):
     t = h_mod_l(R, A_bytes, msg)
     s = (r + t * a) % L
     return R + s.to_bytes(32, "little")
+
+
+def check_comb_table(raw, w):
+    """raw: (rows, entries, 96) uint8 — the fixed-base comb table; asserts entry [j][k] == (k + 1) * 2^(w j) * B as
+    (y+x, y-x, 2dxy), canonical little-endian, for every entry."""
+    rows, entries = raw.shape[0], raw.shape[1]
+    base = B
+    for j in range(rows):
+        acc = base
+        for k in range(entries):
+            x, y = acc
+            want = b"".join(v.to_bytes(32, "little") for v in ((y + x) % P, (y - x) % P, 2 * D * x * y % P))
+            assert raw[j, k].tobytes() == want, (j, k)
+            acc = add(acc, base)
+        for _ in range(w):
+            base = add(base, base)

@@ -8,11 +8,9 @@ extern "C" {
 void h_fe_mul(uint32_t *r, const uint32_t *a, const uint32_t *b) { fe x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_mul(z, x, y); memcpy(r, z.v, 32); }
 void h_fe_sq(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 32); fe_sq(z, x); memcpy(r, z.v, 32); }
 void h_fe_mul121665(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 32); fe_mul121665(z, x); memcpy(r, z.v, 32); }
-void h_fe_carry(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 32); fe_carry(z, x); memcpy(r, z.v, 32); }
 void h_fe_canon(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 32); fe_canon(z, x); memcpy(r, z.v, 32); }
 void h_fe_add(uint32_t *r, const uint32_t *a, const uint32_t *b) { fe x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_add(z, x, y); memcpy(r, z.v, 32); }
 void h_fe_sub(uint32_t *r, const uint32_t *a, const uint32_t *b) { fe x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_sub(z, x, y); memcpy(r, z.v, 32); }
-void h_fe_sub4(uint32_t *r, const uint32_t *a, const uint32_t *b) { fe x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_sub4(z, x, y); memcpy(r, z.v, 32); }
 void h_fe_neg(uint32_t *r, const uint32_t *a) { fe x, z; memcpy(x.v, a, 32); fe_neg(z, x); memcpy(r, z.v, 32); }
 void h_fe_from_bytes(uint32_t *r, const uint8_t *in) { uint32_t w[8]; memcpy(w, in, 32); fe z; fe_from_words(z, w); memcpy(r, z.v, 32); }
 void h_fe_to_bytes(uint8_t *out, const uint32_t *a) { fe x; memcpy(x.v, a, 32); uint32_t w[8]; fe_to_words(w, x); memcpy(out, w, 32); }
@@ -25,7 +23,8 @@ extern "C" {
 void h_sc_reduce512(uint32_t *r, const uint32_t *x) { sc_reduce512(r, x); }
 void h_sc_reduce256(uint32_t *r, const uint32_t *x) { sc_reduce256(r, x); }
 void h_sc_muladd(uint32_t *r, const uint32_t *a, const uint32_t *b, const uint32_t *c) { sc_muladd(r, a, b, c); }
-void h_sc_recode(uint32_t *e, const uint32_t *x) { sc_recode_radix16(e, x); }
+void h_sc_recode(uint32_t *e, const uint32_t *x) { sc_recode_comb(e, x); }
+int h_comb_w(void) { return EDG_COMB_W; }
 }
 #include "../../libeddsa_b200/csrc/sha512.cuh"
 extern "C" {

@@ -23,11 +23,13 @@ def libpath():
 
 def test_secret_kernels_are_constant_time(libpath):
     results = ct_audit.run(libpath)
-    assert {r["kernel"] for r in results} == {"k_x25519", "k_x25519_base", "k_genpub", "k_signILb0", "k_signILb1", "k_sk_convert"}
+    assert {r["kernel"] for r in results} == {"k_x25519", "k_combILi0", "k_combILi1", "k_expand_key", "k_sign_nonceILb0", "k_sign_nonceILb1",
+                                              "k_sign_finishILb0", "k_sign_finishILb1", "k_sk_convert"}
     for r in results:
         assert "error" not in r, r
         assert r["secret_loads"] > 0, f"{r['kernel']}: the audit saw no secret loads (taint source not found)"
-        assert r["instructions_on_secret_data"] > 0.3 * r["instructions"], r["kernel"]
+        # (k_sign_finish hashes public data; the secrets a, r only enter at S = r + t a)
+        assert r["instructions_on_secret_data"] > 0.1 * r["instructions"], r["kernel"]
         assert r["reached"] > 0.95 * r["instructions"], r["kernel"]
         # the batched kernels keep each thread's projective results in per-thread local arrays (scrubbed
         # before exit); the audit then treats EVERY local-memory load as secret, so a PASS also shows that

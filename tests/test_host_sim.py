@@ -64,10 +64,8 @@ def test_fe_arithmetic_on_all_256_bit_inputs(fe):
         assert val(call(fe.h_fe_sq, A)) % P == a * a % P
         assert val(call(fe.h_fe_mul121665, A)) % P == a * 121665 % P
         assert val(call(fe.h_fe_sub, A, B)) % P == (a - b) % P
-        assert val(call(fe.h_fe_sub4, A, B)) % P == (a - b) % P
         assert val(call(fe.h_fe_add, A, B)) % P == (a + b) % P
         assert val(call(fe.h_fe_neg, A)) % P == (-a) % P
-        assert val(call(fe.h_fe_carry, A)) % P == a % P
 
 
 def test_fe_canonical_bytes(fe):
@@ -122,8 +120,12 @@ def test_sc_reduce_muladd_recode(fe):
     for x in [0, 1, L - 1] + [rng.randrange(L) for _ in range(500)]:
         e = (ctypes.c_uint32 * 8)()
         fe.h_sc_recode(e, W(x, 8))
-        ds = [((V(e) >> (4 * j)) & 15) - 8 for j in range(64)]
-        assert all(-8 <= d <= 7 for d in ds) and sum(d * 16**j for j, d in enumerate(ds)) == x
+        w = fe.h_comb_w()                                      # signed radix-2^w digits of the fixed-base comb
+        rows, half = (255 + w - 1) // w, 1 << (w - 1)
+        assert V(e) < 2**256
+        ds = [((V(e) >> (w * j)) & (2 * half - 1)) - half for j in range(rows)]
+        assert V(e) >> (w * rows) == 0
+        assert all(-half <= d < half for d in ds) and sum(d * (2 * half)**j for j, d in enumerate(ds)) == x
 
 
 def test_sha512_prefixed_streams(fe):
@@ -216,6 +218,20 @@ def test_window_tables_host_build(ops):
             assert raw[m, e].tobytes() == wtab_expected(m, e), (m, e)
 
 
+def test_comb_table_host_build(ops):
+    """The fixed-base comb table (k_comb_base / k_comb_rows run this code on the device): entry [j][k] =
+    (k + 1) * 2^(W j) * B in affine precomputed form, every entry against the big-integer model."""
+    import edmodel as em
+    rows, entries = ctypes.c_int(), ctypes.c_int()
+    ops.hs_comb.restype = ctypes.POINTER(ctypes.c_uint32)
+    tab = ops.hs_comb(ctypes.byref(rows), ctypes.byref(entries))
+    rows, entries = rows.value, entries.value
+    w = entries.bit_length()                                   # entries = 2^(w-1)
+    assert rows == (255 + w - 1) // w
+    raw = np.ctypeslib.as_array(tab, shape=(rows, entries, 24)).view(np.uint8).reshape(rows, entries, 96)
+    em.check_comb_table(raw, w)
+
+
 def test_half_gcd(ops):
     """hgcd.cuh: (rho, tau) is a lattice vector (tau = rho t mod 8L), rho is odd, and both are short — for random t,
     for structured t (tiny, huge partial quotients, even-rho traps) and for the documented fallback."""
@@ -246,15 +262,24 @@ def test_half_gcd(ops):
 
 
 def test_batch_inversion(ops):
-    """Montgomery's trick shares one exponentiation among up to 8 values; zeros (any representative)
-    stay zero and do not poison their neighbours (inv(0) = 0)."""
+    """Montgomery's trick shares one exponentiation among up to EDG_BATCH = 32 values (the shipped batch size); zeros
+    (any representative) stay zero and do not poison their neighbours (inv(0) = 0) — including the first
+    and the last element, runs of zeros, and an all-zero batch."""
     rng = random.Random(6)
-    for cnt in range(1, 9):
-        for trial in range(30):
+    for cnt in range(1, 33):
+        for trial in range(12):
             vals = [rng.getrandbits(256) for _ in range(cnt)]
             for j in range(cnt):
                 if rng.random() < 0.25:
                     vals[j] = rng.choice([0, P, 2 * P])
+            if trial == 0:
+                vals[0] = 0
+            elif trial == 1:
+                vals[-1] = P
+            elif trial == 2:
+                vals = [rng.choice([0, P, 2 * P]) for _ in range(cnt)]
+            elif trial == 3 and cnt > 9:
+                vals[9:] = [0] * (cnt - 9)
             buf = ctypes.create_string_buffer(b"".join(v.to_bytes(32, "little") for v in vals))
             ops.hs_batch_inv(buf, cnt)
             for j, v in enumerate(vals):

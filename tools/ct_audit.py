@@ -2,7 +2,7 @@
 """Constant-time SASS audit of the secret-key kernels (sm_100a).
 
 Static taint analysis over the disassembly (cuobjdump -sass) of each kernel that touches a secret
-(k_x25519, k_x25519_base, k_genpub, k_sign<false>, k_sign<true>, k_sk_convert):
+(k_x25519, k_comb<0/1>, k_expand_key, k_sign_nonce<>, k_sign_finish<>, k_sk_convert):
 
   * sources : every value loaded from global memory through a pointer derived from a SECRET kernel
               parameter (the secret key / scalar arrays); everything computed from such values;
@@ -39,10 +39,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # signatures: see libeddsa_b200/csrc/kernels_*.cu   (every parameter is 8 bytes wide)
 SECRET_PARAMS = {
     "k_x25519E": {"params": ["n", "out", "scalar", "point"], "secret": ["scalar"]},
-    "k_x25519_base": {"params": ["n", "out", "scalar"], "secret": ["scalar"]},
-    "k_genpub": {"params": ["n", "pub", "sec"], "secret": ["sec"]},
-    "k_signILb0": {"params": ["n", "sig", "sec", "pub", "msgs", "off", "fixed_len"], "secret": ["sec"]},   # fixed-length batches
-    "k_signILb1": {"params": ["n", "sig", "sec", "pub", "msgs", "off", "fixed_len"], "secret": ["sec"]},   # ragged batches (length-sorted tiles)
+    # the comb kernel shared by genpub / sign (MODE 0: scalars reduced mod L by the hash kernels) and x25519_base (MODE 1)
+    "k_combILi0": {"params": ["n", "out", "out_stride", "scalars", "wipe", "comb_g"], "secret": ["scalars"]},
+    "k_combILi1": {"params": ["n", "out", "out_stride", "scalars", "wipe", "comb_g"], "secret": ["scalars"]},
+    "k_expand_key": {"params": ["n", "a_out", "sec"], "secret": ["sec"]},
+    "k_sign_nonceILb0": {"params": ["n", "a_out", "r_out", "sec", "msgs", "off", "fixed_len"], "secret": ["sec"]},          # fixed-length batches
+    "k_sign_nonceILb1": {"params": ["n", "a_out", "r_out", "sec", "msgs", "off", "fixed_len"], "secret": ["sec"]},          # ragged batches (length-sorted tiles)
+    "k_sign_finishILb0": {"params": ["n", "sig", "a_in", "r_in", "pub", "msgs", "off", "fixed_len"], "secret": ["a_in", "r_in"]},
+    "k_sign_finishILb1": {"params": ["n", "sig", "a_in", "r_in", "pub", "msgs", "off", "fixed_len"], "secret": ["a_in", "r_in"]},
     "k_sk_convert": {"params": ["n", "out", "in"], "secret": ["in"]},
 }
 PUBLIC_KERNELS = ["k_verify", "k_pk_convert"]
