@@ -417,7 +417,7 @@ def run_ours(args):
         achieved = per_gpu * products(OURS_FM["verify"]) / 1e12
         roofline = {
             "bound": "int32-multiply (IMAD.WIDE on the fmaheavy pipe; compute-bound, see DESIGN.md §4)",
-            "kernel": "k_verify_front + k_verify (one pass = %d launches: the two stages per chunk of signatures)" % max(int(launches) // K, 1),
+            "kernel": "k_verify_scalars + k_verify_points + k_verify (one step = %d launches: the three stages per pass of 303 104 signatures)" % max(int(launches) // K, 1),
             "achieved": achieved, "peak": PEAK_TMULS, "unit": "T wide-multiplies/s (32x32->64)", "frac": achieved / PEAK_TMULS,
             "frac_reference_fm": per_gpu * products(REF_FM["verify"]) / 1e12 / PEAK_TMULS,
             "peak_source": "measured: tools/pipe_bench.cu on this pool's B200 = 32 IMAD.WIDE/clk/SM x 148 SM x 1965 MHz (profiles/r01_pipe_microbench.md)",
@@ -426,9 +426,9 @@ def run_ours(args):
             "kernel_ms_per_launch": kernel_ms,
             "stages": ncu_stages(),
             "traffic": ncu_traffic(n),
-            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of both stages from the ncu --set full capture on 2^18 signatures "
-                            "(profiles/r01_ncu_summary.json), scaled to this batch; ~7 KB/signature = the 2.4 KB record the front stage "
-                            "hands to the window loop (two 8-entry point tables), written once and read back ~2x: 5 % of HBM bandwidth",
+            "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of the three stages from the ncu --set full capture on 2^18 signatures "
+                            "(profiles/r02_ncu_summary.json), scaled to this batch; the 2.4 KB record the front stages hand to the window "
+                            "loop (two 8-entry point tables) is written once and read back ~2x: ~5 % of HBM bandwidth",
             "hbm": {"algorithmic_bytes_per_launch": n * IO_BYTES["verify"],
                     "achieved_gbs": n * IO_BYTES["verify"] / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak(),
                     "note": "HBM is not the bound: <0.1 % of measured copy bandwidth"},
@@ -510,24 +510,27 @@ def run_inproc(world):
         return {"error": repr(e)}
 
 
+VERIFY_STAGES = ("verify_scalars", "verify_points", "verify_loop")
+
+
 def ncu_traffic(n):
     """DRAM bytes per pass over n signatures, from the committed ncu capture (None if it is not there)."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-        per_op = sum(d[k]["dram_read_bytes"] + d[k]["dram_write_bytes"] for k in ("verify_loop", "verify_front")) / d["ops_per_launch"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+        per_op = sum(d[k]["dram_read_bytes"] + d[k]["dram_write_bytes"] for k in VERIFY_STAGES) / d["ops_per_launch"]
         return int(per_op * n)
     except Exception:
         return None
 
 
 def ncu_stages():
-    """The two kernels of a verify pass as captured by ncu on 2^18 signatures (profiles/r01_ncu_summary.json): share of the
+    """The three kernels of a verify pass as captured by ncu on 2^18 signatures (profiles/r02_ncu_summary.json): share of the
     pass and multiplier-pipe utilisation of each — context for the pass-level roofline above, not measured live."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")))
-        tot = d["verify_front"]["duration_ms"] + d["verify_loop"]["duration_ms"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_summary.json")))
+        tot = sum(d[k]["duration_ms"] for k in VERIFY_STAGES)
         return {d[k]["kernel"]: {"share_of_pass": round(d[k]["duration_ms"] / tot, 3), "fmaheavy_pipe_busy_pct": d[k]["fmaheavy_pipe_busy_pct"],
-                                 "registers": d[k]["registers_per_thread"]} for k in ("verify_front", "verify_loop")}
+                                 "registers": d[k]["registers_per_thread"]} for k in VERIFY_STAGES}
     except Exception:
         return None
 

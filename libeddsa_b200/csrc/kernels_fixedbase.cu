@@ -41,6 +41,14 @@ __device__ __forceinline__ void store_words8(u32 *dst, const u32 w[8]) {
     p[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// Scratch that a kernel reads AND overwrites (the wipe) must not go through the read-only data path: ld.global.nc tells
+// the compiler the memory never changes during the kernel, so it may sink such a load below the wipe and read zeros.
+__device__ __forceinline__ void load_scratch8(u32 w[8], const u32 *src) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    const uint4 a = p[0], b = p[1];
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+
 __device__ __forceinline__ void wipe_words8(u32 *dst) {
     volatile uint4 *p = reinterpret_cast<volatile uint4 *>(dst);
     p[0].x = 0; p[0].y = 0; p[0].z = 0; p[0].w = 0; p[1].x = 0; p[1].y = 0; p[1].z = 0; p[1].w = 0;
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n
             const size_t i = i0 + (size_t)k * T;
             if (i >= n) break;
             u32 x[8];
-            load_words8(x, scalars + 8 * i);
+            load_scratch8(x, scalars + 8 * i);
             if (wipe) wipe_words8(scalars + 8 * i);            // (public flag) this kernel is the last reader of the scalar
             if (MODE == 1) {
                 u32 e[8];
@@ -109,7 +117,7 @@ __global__ void __launch_bounds__(kThreads) k_expand_key(size_t n, u32 *a_out, c
 // neighbouring lanes get messages of neighbouring lengths.  Lengths are public.
 template <bool RAGGED, typename F>
 __device__ __forceinline__ void for_each_message(size_t n, const unsigned long long *off, F body) {
-    if (!RAGGED) {
+    if constexpr (!RAGGED) {
         for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) body(i);
     } else {
         __shared__ u32 s_key[kMsgTile];
@@ -147,15 +155,17 @@ __global__ void __launch_bounds__(kThreads) k_sign_finish(size_t n, uint8_t *sig
     for_each_message<RAGGED>(n, off, [&](size_t i) {
         const uint8_t *m; u64 len;
         msg_of(m, len, msgs, off, fixed_len, i);
-        u32 a[8], r[8], R[8], p[8], S[8];
-        load_words8(a, a_in + 8 * i);
-        load_words8(r, r_in + 8 * i);
+        u32 R[8], p[8], t[8];
+        load_scratch8(R, reinterpret_cast<const u32 *>(sig + 64 * i));     // (sig is written below: not read-only either)
+        load8(p, pub, i);
+        ed25519_sign_challenge(t, R, p, m, len);               // public data only
+        u32 a[8], r[8], S[8];
+        load_scratch8(a, a_in + 8 * i);                        // the secrets enter here
+        load_scratch8(r, r_in + 8 * i);
+        sc_muladd(S, t, a, r);
+        store8(sig, 2 * i + 1, S);
         wipe_words8(a_in + 8 * i);
         wipe_words8(r_in + 8 * i);
-        load8(R, sig, 2 * i);
-        load8(p, pub, i);
-        ed25519_sign_finish(S, a, r, R, p, m, len);
-        store8(sig, 2 * i + 1, S);
     });
 }
 

@@ -212,8 +212,9 @@ EDG_HD void ed25519_sign_nonce(u32 a[8], u32 r[8], const uint8_t *sk, const uint
     sc_reduce512(r, h);
 }
 
-EDG_HD void ed25519_sign_finish(u32 S[8], const u32 a[8], const u32 r[8], const u32 Renc[8], const u32 pub[8], const uint8_t *msg, u64 len) {
-    u32 t[8], h[16];
+// t = H(R || pub || M) mod L — public data only; the secrets a, r enter afterwards in S = r + t a (sc_muladd)
+EDG_HD void ed25519_sign_challenge(u32 t[8], const u32 Renc[8], const u32 pub[8], const uint8_t *msg, u64 len) {
+    u32 h[16];
     u64 pre[8], st[8];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -223,7 +224,6 @@ EDG_HD void ed25519_sign_finish(u32 S[8], const u32 a[8], const u32 r[8], const 
     sha512_prefixed<8>(st, pre, msg, len);
     sha512_state_to_le_words(h, st);
     sc_reduce512(t, h);
-    sc_muladd(S, t, a, r);
 }
 
 EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], const uint8_t *msg, u64 len, const u32 *comb) {
@@ -233,7 +233,9 @@ EDG_HD void ed25519_sign_op(u32 sig[16], const uint8_t *sk, const u32 pub[8], co
     ge_scalarmult_base_ct(R, r, comb);
     fe_inv(R.Z, R.Z);
     ge_tobytes_zinv(sig, R.X, R.Y, R.Z);
-    ed25519_sign_finish(sig + 8, a, r, sig, pub, msg, len);
+    u32 t[8];
+    ed25519_sign_challenge(t, sig, pub, msg, len);
+    sc_muladd(sig + 8, t, a, r);
 }
 
 // out = u-coordinate of (clamp(scalar) mod L) * B                     [do_x25519_base, x25519.c:158-197]

@@ -421,7 +421,7 @@ def test_device_pointer_api_matches_host_api(ed):
     ed.ed25519_sign_batch_dev(sig_t, sec_t, pub_t, msg_t, fixed_len=64)
     ed.ed25519_verify_batch_dev(ok_t, sig_t, pub_t, msg_t, fixed_len=64)
     torch.cuda.synchronize()
-    assert ed.launch_count() - before == 7              # genpub: hash + comb; sign: nonce + comb + finish; verify: front + window loop
+    assert ed.launch_count() - before == 8              # genpub: hash + comb; sign: nonce + comb + finish; verify: scalars + points + window loop
     pub = ed.ed25519_genpub_batch(sec)
     assert (pub_t.cpu().numpy() == pub).all()
     assert (sig_t.cpu().numpy() == ed.ed25519_sign_batch(sec, pub, msgs, fixed_len=64)).all()
