@@ -55,7 +55,7 @@ OURS_FM_SINGLE = {"sign": (369, 254), "genpub": (369, 254), "x25519_base": (368,
 # the kernels share one inversion (254 S + 11 M) among up to EDG_BATCH = 32 operations of a thread, +3 M per operation;
 # a thread of the persistent grid gets n / (resident threads) operations, so at 2^20 per GPU the share is 14..28
 EDG_BATCH = 32
-RESIDENT_THREADS = {"sign": 2 * 148 * 256, "genpub": 2 * 148 * 256, "x25519_base": 2 * 148 * 256, "x25519": 4 * 148 * 128}   # k_comb: 2 x 256 threads per SM
+RESIDENT_THREADS = {"sign": 148 * 512, "genpub": 148 * 512, "x25519_base": 148 * 512, "x25519": 4 * 148 * 128}   # k_comb: one block of 512 threads per SM
 
 
 def ours_fm(op, n=1 << 20):

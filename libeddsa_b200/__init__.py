@@ -216,9 +216,8 @@ def comb_table():
     got = lib().eddsa_b200_comb_table(_p(buf), buf.nbytes)
     if got == 0 or got % 96:
         raise EddsaB200Error(f"eddsa_b200_comb_table returned {got}: " + lib().eddsa_b200_last_error().decode(errors="replace"))
-    cells = got // 96
-    entries = 16 if cells % 16 == 0 and 255 // 5 + 1 == cells // 16 else 8       # W = 5: 51 x 16, W = 4: 64 x 8
-    return buf[:got].reshape(cells // entries, entries, 96).copy()
+    shape = {51 * 16: (51, 16), 64 * 8: (64, 8)}[got // 96]                      # comb window W = 5 / W = 4 (sc.cuh: EDG_COMB_W)
+    return buf[:got].reshape(shape + (96,)).copy()
 
 
 def peek_staging(which, slot, length):

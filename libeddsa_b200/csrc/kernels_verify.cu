@@ -30,7 +30,7 @@ using namespace edg;
 #define EDG_LB_VLOOP EDG_LB_VERIFY
 #endif
 #ifndef EDG_MSG_TILE
-#define EDG_MSG_TILE 2048   /* ragged batches: consecutive signatures sorted by message length together */
+#define EDG_MSG_TILE 512    /* ragged batches: consecutive signatures sorted by message length together */
 #endif
 namespace {
 constexpr int kVThreads = EDG_VTHREADS;

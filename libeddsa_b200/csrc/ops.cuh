@@ -142,14 +142,17 @@ EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
     u32 e[8];
     sc_recode_comb(e, x);
     ge_identity(r);
-#pragma unroll 1
-    for (int j = 0; j < EDG_COMB_ROWS; j++) {
+    auto next_digit = [&e]() -> int {
         const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
 #pragma unroll
         for (int i = 0; i < 7; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
         e[7] >>= EDG_COMB_W;
+        return digit;
+    };
+#pragma unroll 1
+    for (int j = 0; j < EDG_COMB_ROWS; j++) {
         ge_pre t;
-        ge_pre_select_ct<EDG_COMB_ENTRIES>(t, comb + j * (EDG_COMB_ENTRIES * 24), digit);
+        ge_pre_select_ct<EDG_COMB_ENTRIES>(t, comb + j * (EDG_COMB_ENTRIES * 24), next_digit());
         ge_madd(r, r, t, j + 1 < EDG_COMB_ROWS);              // (public loop position) the last addition needs no T
     }
 }

@@ -258,12 +258,16 @@ rng = np.random.default_rng(9)
 n = 150000                                                        # 3 chunks of >= 65536: every pipeline slot gets used
 sec = rng.integers(1, 256, (n, 32), dtype=np.uint8); pts = rng.integers(1, 256, (n, 32), dtype=np.uint8)
 msgs = rng.integers(1, 256, (n, 16), dtype=np.uint8)
+chunks = [65536, 65536, n - 2 * 65536]                           # host.c: run_shard cuts n into chunks of max(n / 4, 65536); slot = chunk
 def residue(width_in, width_out):
+    # non-zero bytes left where each chunk's first input array (the secrets) and its outputs were staged
     r = []
-    for slot in range(3):
+    for slot, m in enumerate(chunks):
         for which, w in ((0, width_in), (1, width_in), (2, width_out), (3, width_out)):
-            b = ed.peek_staging(which, slot, 65536 * w)
-            r.append(int(np.count_nonzero(b)))
+            if w:
+                b = ed.peek_staging(which, slot, m * w)
+                assert len(b) == m * w
+                r.append(int(np.count_nonzero(b)))
     return r
 pub = ed.ed25519_genpub_batch(sec);                r_genpub = residue(32, 0)
 sig = ed.ed25519_sign_batch(sec, pub, msgs, fixed_len=16); r_sign = residue(32, 0)

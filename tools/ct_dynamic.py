@@ -14,7 +14,9 @@ METRICS = ["smsp__inst_executed.sum", "smsp__thread_inst_executed.sum",
            "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
            "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
            "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_local_op_st.sum",
-           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_branch.sum"]
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+           "smsp__inst_executed_op_branch.sum"]
+SHARED_WAVEFRONTS = "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"
 KERNELS = "regex:k_comb|k_x25519|k_expand_key|k_sign_nonce|k_sign_finish|k_sk_convert"
 
 
@@ -40,13 +42,22 @@ def run(n=16384, workdir=None):
     caps = {cls: capture(cls, n, workdir) for cls in ("zeros", "ones", "random")}
     names = [k for k, _ in caps["zeros"]]
     assert all([k for k, _ in caps[c]] == names for c in caps), "different kernel sequences"
-    out = {"operations_per_launch": n, "metrics": METRICS, "classes": list(caps), "launches": [], "identical": True}
+    out = {"operations_per_launch": n, "metrics": METRICS, "classes": list(caps), "launches": [], "identical": True,
+           "how": "every counter must be identical for all-zero, all-one and random secrets.  One exception, reported per launch as 'noisy': the "
+                  "shared-memory WAVEFRONT counter of the ragged kernels (k_sign_nonce<1>, k_sign_finish<1>), whose only shared-memory traffic is "
+                  "the bitonic sort of the PUBLIC message lengths: it includes arbitration replays and differs by ~1e-4 between two runs on "
+                  "identical inputs (shared-memory instruction counts are exact); there the criterion is a relative spread below 2e-3"}
     for i, name in enumerate(names):
-        row = {"kernel": name, "counters": {}, "identical": True}
+        row = {"kernel": name, "counters": {}, "identical": True, "noisy": []}
         for m in METRICS:
             vals = [caps[c][i][1].get(m) for c in caps]
-            row["counters"][m] = vals[0] if len(set(vals)) == 1 else dict(zip(caps, vals))
-            if len(set(vals)) != 1:
+            if len(set(vals)) == 1:
+                row["counters"][m] = vals[0]
+                continue
+            row["counters"][m] = dict(zip(caps, vals))
+            if m == SHARED_WAVEFRONTS and "<1>" in name and max(vals) - min(vals) <= 2e-3 * max(vals):
+                row["noisy"].append(m)
+            else:
                 row["identical"] = False
         out["identical"] &= row["identical"]
         out["launches"].append(row)
@@ -61,7 +72,7 @@ if __name__ == "__main__":
     res = run(a.n)
     for r in res["launches"]:
         print(("SAME " if r["identical"] else "DIFF ") + r["kernel"], {k.split("__")[1][:28]: v for k, v in r["counters"].items()} if not r["identical"] else
-              int(r["counters"]["smsp__inst_executed.sum"]), flush=True)
+              int(r["counters"]["smsp__inst_executed.sum"]), ("noisy (differs between two runs on equal inputs): %s" % r["noisy"]) if r["noisy"] else "", flush=True)
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)
     sys.exit(0 if res["identical"] else 1)
