@@ -182,6 +182,64 @@ EDG_HD void ge_pre_select_ct(ge_pre &t, const u32 *row, int digit) {
     ge_pre_scan_finish(t, s);
 }
 
+#define EDG_XCHG_STRIDE 28     /* words per lane in a warp's exchange area of ge_pre_select_mma (16-byte aligned, conflict-free reads) */
+#if defined(__CUDA_ARCH__)
+// The same constant-time lookup as ONE-HOT x TABLE contraction on the tensor cores (device only, warp-synchronous: all 32
+// lanes must call).  Scanning 16 entries x 24 words with masks costs 384 LOP3 + 96 LDS.128 per lookup — half of the ALU
+// work of a fixed-base operation, and the comb kernel is held back by exactly that (multiplier pipe 59 % busy, ALU pipe
+// 46 %).  Here lane L contributes the one-hot row [|digit_L| == k + 1], k = 0..15, of a 32 x 16 matrix A (u8), the table row is
+// a 16 x 96 matrix B of bytes, and D = A B (s32, exact: one byte per sum) holds the selected entry of every lane:
+// 24 x mma.sync.m16n8k16.u8.u8 per warp.  Still constant time: every entry takes part in every product, and no address
+// or branch depends on a digit (the digits only ever travel as DATA: shuffles, mma operands, shared-memory stores at
+// lane-indexed addresses).
+//   row_mma : this row in fragment order (built by k_comb_layout): word [nt * 32 + lane] = bytes of entries 4q .. 4q+3
+//             (q = lane % 4) at column lane / 4 of byte-tile nt; column (nt = 2m + s, n = 2q' + b) is entry byte
+//             4 (6 q' + m) + 2 s + b, chosen so that a thread's results of two neighbouring tiles form one complete word
+//   xchg    : this warp's exchange area in shared memory, 32 lanes x EDG_XCHG_STRIDE words (results come out spread over
+//             the four threads of a quad and are handed to their lane through it)
+__device__ __forceinline__ void ge_pre_select_mma(ge_pre &t, const u32 *row_mma, int digit, u32 *xchg) {
+    const u32 lane = threadIdx.x & 31u, g = lane >> 2, q = lane & 3u;
+    const u32 neg = ct_mask((u32)(digit >> 31));         // all-ones if digit < 0
+    const u32 absd = ((u32)digit ^ neg) - neg;           // 0 .. 16
+    u32 a[4];                                            // one-hot bytes k = 4q .. 4q+3 of rows (lanes) g, g+8, g+16, g+24
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const u32 x = __shfl_sync(0xffffffffu, absd, (int)(g + 8u * r)) - 1u - 4u * q;     // 0..3 iff that lane's entry is one of ours
+        const u32 hit = 0u - ((((x >> 2) - 1u) >> 31));                                       // all-ones iff x < 4
+        a[r] = (1u << ((x & 3u) * 8u)) & hit;
+    }
+    __syncwarp();                                        // the previous lookup's results have been read by every lane
+#pragma unroll
+    for (int m = 0; m < 6; m++) {
+        const u32 b0 = row_mma[(2 * m) * 32 + lane], b1 = row_mma[(2 * m + 1) * 32 + lane];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            int d0[4], d1[4];
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                : "=r"(d0[0]), "=r"(d0[1]), "=r"(d0[2]), "=r"(d0[3]) : "r"(a[2 * mt]), "r"(a[2 * mt + 1]), "r"(b0), "r"(0));
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                : "=r"(d1[0]), "=r"(d1[1]), "=r"(d1[2]), "=r"(d1[3]) : "r"(a[2 * mt]), "r"(a[2 * mt + 1]), "r"(b1), "r"(0));
+            // (c0, c1): row g + 16 mt, (c2, c3): row g + 8 + 16 mt; columns 2q, 2q+1 -> word 6q + m of that lane's entry
+            const u32 lo = __byte_perm(__byte_perm((u32)d0[0], (u32)d0[1], 0x0040), __byte_perm((u32)d1[0], (u32)d1[1], 0x0040), 0x5410);
+            const u32 hi = __byte_perm(__byte_perm((u32)d0[2], (u32)d0[3], 0x0040), __byte_perm((u32)d1[2], (u32)d1[3], 0x0040), 0x5410);
+            xchg[(g + 16u * mt) * EDG_XCHG_STRIDE + 6u * q + m] = lo;
+            xchg[(g + 8u + 16u * mt) * EDG_XCHG_STRIDE + 6u * q + m] = hi;
+        }
+    }
+    __syncwarp();
+    u32 w[24];
+    const uint4 *mine = reinterpret_cast<const uint4 *>(xchg + lane * EDG_XCHG_STRIDE);
+#pragma unroll
+    for (int i = 0; i < 6; i++) { const uint4 v = mine[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+    const u32 zero = (absd - 1u) >> 31;                  // digit 0: the neutral element (1, 1, 0) instead of all zeros
+    w[0] |= zero;
+    w[8] |= zero;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { t.ypx.v[i] = w[i]; t.ymx.v[i] = w[8 + i]; t.xy2d.v[i] = w[16 + i]; }
+    ge_pre_cneg(t, neg);
+}
+#endif
+
 // Decompress 32 bytes (8 LE words) into an affine point (Z = 1).  Never fails, exactly like the
 // reference: bit 255 is the sign, the low 255 bits are y and are NOT range-checked (y >= p is
 // reduced), x = 0 with sign 1 stays 0.  Returns the all-ones mask if (x, y) is on the curve; for an

@@ -28,10 +28,13 @@ using namespace edg;
 #define EDG_MSG_TILE 512         /* ragged batches: consecutive operations sorted by message length together (4 per thread: small
                                     tiles keep enough blocks in flight — a verify pass of 303 104 signatures is 592 tiles) */
 #endif
+#ifndef EDG_COMB_MMA
+#define EDG_COMB_MMA (EDG_COMB_W == 5)   /* table lookups as one-hot x table products on the tensor cores (ge.cuh) */
+#endif
 namespace {
 
 constexpr int kCombThreads = EDG_COMB_THREADS;
-constexpr int kCombBytes = EDG_COMB_WORDS * 4;
+constexpr int kCombBytes = EDG_COMB_WORDS * 4 + (EDG_COMB_MMA ? (EDG_COMB_THREADS / 32) * 32 * EDG_XCHG_STRIDE * 4 : 0);
 constexpr size_t kPass = (size_t)1 << EDG_FIXEDBASE_PASS_LOG2;
 constexpr int kMsgTile = EDG_MSG_TILE;
 constexpr int kMsgTileBits = kMsgTile == 512 ? 9 : kMsgTile == 1024 ? 10 : kMsgTile == 2048 ? 11 : 12;
@@ -62,19 +65,25 @@ __device__ __forceinline__ void wipe_words8(u32 *dst) {
 template <int MODE>
 __global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n, uint8_t *out, unsigned out_stride, u32 *scalars, int wipe,
                                                                       const u32 *__restrict__ comb_g) {
-    extern __shared__ __align__(16) u32 s_comb[];
+    extern __shared__ __align__(16) u32 s_comb[];                // the table | one exchange area per warp (EDG_COMB_MMA)
     stage_table(s_comb, comb_g, EDG_COMB_WORDS);
+#if EDG_COMB_MMA
+    u32 *xchg = s_comb + EDG_COMB_WORDS + (threadIdx.x >> 5) * (32 * EDG_XCHG_STRIDE);
+#endif
     const size_t T = (size_t)gridDim.x * blockDim.x;
-    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T * EDG_BATCH) {
+    // whole warps stay together (the tensor-core lookup is warp-synchronous): lanes past the end of the batch redo the
+    // last operation and drop the result
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; (i0 & ~(size_t)31) < n; i0 += T * EDG_BATCH) {
         fe U[EDG_BATCH], V[MODE == 0 ? EDG_BATCH : 1], Z[EDG_BATCH];     // MODE 0: X, Y, Z;  MODE 1: Z + Y, -, Z - Y
         int cnt = 0;
 #pragma unroll 1
         for (int k = 0; k < EDG_BATCH; k++) {
             const size_t i = i0 + (size_t)k * T;
-            if (i >= n) break;
+            if ((i & ~(size_t)31) >= n) break;                 // (warp-uniform)
+            const bool live = i < n;
+            const size_t src = live ? i : n - 1;
             u32 x[8];
-            load_scratch8(x, scalars + 8 * i);
-            if (wipe) wipe_words8(scalars + 8 * i);            // (public flag) this kernel is the last reader of the scalar
+            load_scratch8(x, scalars + 8 * src);
             if (MODE == 1) {
                 u32 e[8];
 #pragma unroll
@@ -83,10 +92,14 @@ __global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n
                 sc_reduce256(x, e);                            // Q9
             }
             ge_p3 R;
+#if EDG_COMB_MMA
+            ge_scalarmult_base_ct_mma(R, x, s_comb, xchg);
+#else
             ge_scalarmult_base_ct(R, x, s_comb);
+#endif
             if (MODE == 0) { fe_copy(U[k], R.X); fe_copy(V[k], R.Y); fe_copy(Z[k], R.Z); }
             else { fe_add(U[k], R.Z, R.Y); fe_sub(Z[k], R.Z, R.Y); }                       // x25519.c:190-194
-            cnt++;
+            cnt += live ? 1 : 0;
         }
         fe_batch_inv(Z, cnt);
 #pragma unroll 1
@@ -102,6 +115,28 @@ __global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n
         scrub(V, MODE == 0 ? EDG_BATCH : 1);
         scrub(Z, EDG_BATCH);
     }
+    // the scalars are wiped once every thread is past its last read: a lane past the end re-reads ANOTHER lane's scalar
+    if (wipe) {
+        __syncthreads();
+        // (grid-wide ordering is not needed: only lanes of the last warp of the batch re-read a scalar, and it belongs to
+        //  their own warp)
+        for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += T) wipe_words8(scalars + 8 * i0);
+    }
+}
+
+// comb table in fragment order for ge_pre_select_mma: word [row][nt][lane] = bytes of entries 4q .. 4q+3 (q = lane % 4) at
+// entry byte 4 (6 (g / 2) + nt / 2) + 2 (nt % 2) + g % 2, g = lane / 4
+__global__ void k_comb_layout(u32 *mma, const u32 *table) {
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= EDG_COMB_WORDS) return;
+    const unsigned row = idx / (EDG_COMB_ENTRIES * 24), rem = idx % (EDG_COMB_ENTRIES * 24), nt = rem / 32, lane = rem % 32;
+    const unsigned g = lane >> 2, q = lane & 3, byte = 4 * (6 * (g / 2) + nt / 2) + 2 * (nt % 2) + g % 2;
+    u32 w = 0;
+    for (unsigned i = 0; i < 4; i++) {
+        const u32 *entry = table + ((size_t)row * EDG_COMB_ENTRIES + 4 * q + i) * 24;
+        w |= ((entry[byte >> 2] >> (8 * (byte & 3))) & 0xffu) << (8 * i);
+    }
+    mma[idx] = w;
 }
 
 // a[i] = clamp(SHA512(sec[i])[0..31]) mod L                                     [ed25519_key_setup, ed25519-sha512.c:31-47, :62]
@@ -212,7 +247,9 @@ int edg_kernels_init(void) {
 }
 
 size_t edg_comb_table_payload_bytes(void) { return (size_t)EDG_COMB_WORDS * sizeof(u32); }
-size_t edg_comb_table_bytes(void) { return ((size_t)EDG_COMB_WORDS + 24u * EDG_COMB_ROWS) * sizeof(u32); }   // + the row base points
+// device allocation: the table | the row base points | the table in fragment order (what the kernels stage when EDG_COMB_MMA)
+size_t edg_comb_table_bytes(void) { return (2 * (size_t)EDG_COMB_WORDS + 24u * EDG_COMB_ROWS) * sizeof(u32); }
+static const u32 *comb_for_kernels(const void *table) { return (const u32 *)table + (EDG_COMB_MMA ? EDG_COMB_WORDS + 24u * EDG_COMB_ROWS : 0); }
 void edg_comb_geometry(int *rows, int *entries) { *rows = EDG_COMB_ROWS; *entries = EDG_COMB_ENTRIES; }
 
 int edg_comb_table_init(void *table, void *stream) {
@@ -220,6 +257,7 @@ int edg_comb_table_init(void *table, void *stream) {
     k_comb_base<<<1, EDG_COMB_ROWS, 0, (cudaStream_t)stream>>>(bases);
     const unsigned groups = EDG_COMB_ROWS * (EDG_COMB_ENTRIES / 8);
     k_comb_rows<<<(groups + 63) / 64, 64, 0, (cudaStream_t)stream>>>(t, bases);
+    k_comb_layout<<<(EDG_COMB_WORDS + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bases + 24 * EDG_COMB_ROWS, t);
     return (int)cudaGetLastError();
 }
 
@@ -228,7 +266,7 @@ size_t edg_fixedbase_scratch_bytes(int is_sign, size_t n) { return (n < kPass ? 
 
 int edg_launch_x25519_base(size_t n, uint8_t *out, const uint8_t *scalar, const void *comb, int sm_count, void *stream) {
     if (n == 0) return 0;
-    k_comb<1><<<comb_grid(n, sm_count), kCombThreads, kCombBytes, (cudaStream_t)stream>>>(n, out, 32u, (u32 *)scalar, 0, (const u32 *)comb);
+    k_comb<1><<<comb_grid(n, sm_count), kCombThreads, kCombBytes, (cudaStream_t)stream>>>(n, out, 32u, (u32 *)scalar, 0, comb_for_kernels(comb));
     return (int)cudaGetLastError();
 }
 
@@ -238,7 +276,7 @@ int edg_launch_genpub(size_t n, uint8_t *pub, const uint8_t *sec, void *scratch,
     for (size_t first = 0; first < n; first += kPass) {
         const size_t m = n - first < kPass ? n - first : kPass;
         k_expand_key<<<msg_grid(k_expand_key, m, false, sm_count), kThreads, 0, st>>>(m, a, sec + 32 * first);
-        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, pub + 32 * first, 32u, a, 1, (const u32 *)comb);
+        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, pub + 32 * first, 32u, a, 1, comb_for_kernels(comb));
         *launches += 2;
     }
     return (int)cudaGetLastError();
@@ -255,7 +293,7 @@ int edg_launch_sign(size_t n, uint8_t *sig, const uint8_t *sec, const uint8_t *p
         const unsigned long long *op = off ? off + first : nullptr;
         if (off) k_sign_nonce<true><<<msg_grid(k_sign_nonce<true>, m, true, sm_count), kThreads, 0, st>>>(m, a, r, sec + 32 * first, mp, op, fixed_len);
         else k_sign_nonce<false><<<msg_grid(k_sign_nonce<false>, m, false, sm_count), kThreads, 0, st>>>(m, a, r, sec + 32 * first, mp, op, fixed_len);
-        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, sig + 64 * first, 64u, r, 0, (const u32 *)comb);
+        k_comb<0><<<comb_grid(m, sm_count), kCombThreads, kCombBytes, st>>>(m, sig + 64 * first, 64u, r, 0, comb_for_kernels(comb));
         if (off) k_sign_finish<true><<<msg_grid(k_sign_finish<true>, m, true, sm_count), kThreads, 0, st>>>(m, sig + 64 * first, a, r, pub + 32 * first, mp, op, fixed_len);
         else k_sign_finish<false><<<msg_grid(k_sign_finish<false>, m, false, sm_count), kThreads, 0, st>>>(m, sig + 64 * first, a, r, pub + 32 * first, mp, op, fixed_len);
         *launches += 3;

@@ -157,6 +157,27 @@ EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
     }
 }
 
+#if defined(__CUDA_ARCH__)
+// The kernels' form: the same comb with the table lookups on the tensor cores (ge.cuh: ge_pre_select_mma).  Warp-
+// synchronous: all 32 lanes of the warp must be here.  comb_mma: the table in fragment order (EDG_COMB_WORDS words).
+__device__ __forceinline__ void ge_scalarmult_base_ct_mma(ge_p3 &r, const u32 x[8], const u32 *comb_mma, u32 *xchg) {
+    static_assert(EDG_COMB_ENTRIES == 16, "the tensor-core lookup is written for the 16-entry rows of the radix-32 comb");
+    u32 e[8];
+    sc_recode_comb(e, x);
+    ge_identity(r);
+#pragma unroll 1
+    for (int j = 0; j < EDG_COMB_ROWS; j++) {
+        const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
+#pragma unroll
+        for (int i = 0; i < 7; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
+        e[7] >>= EDG_COMB_W;
+        ge_pre t;
+        ge_pre_select_mma(t, comb_mma + j * (EDG_COMB_ENTRIES * 24), digit, xchg);
+        ge_madd(r, r, t, j + 1 < EDG_COMB_ROWS);
+    }
+}
+#endif
+
 // clamp as ed25519_key_setup / do_x25519_base do                    [ed25519-sha512.c:41-46, x25519.c:170-172]
 EDG_HD void clamp_words(u32 w[8]) {
     w[0] &= 0xfffffff8u;

@@ -45,4 +45,20 @@ __global__ void k_clean_select(size_t n, uint32_t *out, const uint8_t *sec, cons
     }
     out[i] = r;
 }
+// a secret handed to ANOTHER lane through shared memory and used as a table index there: the audit lets secrets be
+// stored to shared memory (the tensor-core lookup does) but must treat every later shared load as secret
+__global__ void k_leaky_smem(size_t n, uint32_t *out, const uint8_t *sec, const uint32_t *table) {
+    __shared__ uint32_t s[128];
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    s[threadIdx.x & 127] = i < n ? sec[i] : 0;
+    __syncthreads();
+    if (i < n) out[i] = table[s[(threadIdx.x + 1) & 127] & 15];
+}
+// a secret-dependent source lane of a shuffle
+__global__ void k_leaky_shfl(size_t n, uint32_t *out, const uint8_t *sec, const uint32_t *table) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    uint32_t v = table[threadIdx.x & 15], e = i < n ? sec[i] : 0;
+    v = __shfl_sync(0xffffffffu, v, (int)(e & 31));
+    if (i < n) out[i] = v;
+}
 }

@@ -43,7 +43,7 @@ def test_audit_detects_leaks(tmp_path):
     obj = tmp_path / "leaky.o"
     subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-c",
                     os.path.join(ROOT, "tests", "ct_negative", "leaky.cu"), "-o", str(obj)], check=True)
-    spec = {name: {"params": ["n", "out", "sec", "table"], "secret": ["sec"]} for name in ("k_leaky_index", "k_leaky_branch", "k_naive_select", "k_clean_select")}
+    spec = {name: {"params": ["n", "out", "sec", "table"], "secret": ["sec"]} for name in ("k_leaky_index", "k_leaky_branch", "k_naive_select", "k_clean_select", "k_leaky_smem", "k_leaky_shfl")}
     res = {r["kernel"]: r for r in ct_audit.run(str(obj), specs=spec)}
     kinds = lambda k: {v["kind"] for v in res[k]["violations"]}
     assert "secret-dependent memory address / predicate" in kinds("k_leaky_index")
@@ -51,3 +51,6 @@ def test_audit_detects_leaks(tmp_path):
     # nvcc compiles the naive mask idiom into secret-predicated loads; the audit must notice
     assert all(v["kind"] == "secret-dependent memory address / predicate" for v in res["k_naive_select"]["violations"])
     assert res["k_clean_select"]["violations"] == [] and res["k_clean_select"]["secret_loads"] > 0
+    # secrets may travel through shared memory and shuffles as data, never as an index or a lane number
+    assert "secret-dependent memory address / predicate" in kinds("k_leaky_smem") and res["k_leaky_smem"]["shared_memory_holds_secrets"]
+    assert "secret-dependent shuffle lane" in kinds("k_leaky_shfl")

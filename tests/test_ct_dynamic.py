@@ -25,5 +25,5 @@ def test_secret_kernels_have_secret_independent_counters(tmp_path):
     kernels = {r["kernel"] for r in res["launches"]}
     for k in ("k_comb<0>", "k_comb<1>", "k_x25519", "k_expand_key", "k_sign_nonce<0>", "k_sign_nonce<1>", "k_sign_finish<0>", "k_sign_finish<1>", "k_sk_convert"):
         assert any(k in name for name in kernels), (k, kernels)
-    bad = [r for r in res["launches"] if not r["identical"]]
+    bad = [(r["kernel"], m.split("__")[1], v) for r in res["launches"] if not r["identical"] for m, v in r["counters"].items() if isinstance(v, dict)]
     assert not bad, bad

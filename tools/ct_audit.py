@@ -12,7 +12,9 @@ Static taint analysis over the disassembly (cuobjdump -sass) of each kernel that
                   registers or guard predicate are tainted,
               (3) variable-latency arithmetic (MUFU, integer/FP division helpers, I2F/F2I ...) on
                   tainted operands,
-              (4) a tainted value stored to shared memory (would make later shared loads secret).
+              (4) shared memory: a tainted value may be STORED to shared memory at an untainted address (the tensor-core
+                  table lookup hands each lane its entry through a lane-indexed exchange area), but from then on EVERY
+                  shared-memory load is treated as secret, exactly like the stack.
   The analysis is flow-sensitive (per-instruction register / predicate / uniform-register state,
   iterated to a fixed point over the control-flow graph including CALL/RET edges) and conservative:
   a guard-predicated write merges the old and new taint, RET goes to every call-return site, BRX is
@@ -202,6 +204,16 @@ def classify(ins):
     if base in BRANCH_OPS or base in ("BSSY", "BAR", "NOP", "DEPBAR", "MEMBAR", "ERRBAR", "BMOV", "CCTL", "FENCE", "ACQBULK"):
         srcs = [r for t in ops for r in regs_in(t)]
         return dests, srcs, addr, data
+    if base in ("IMMA", "HMMA"):
+        # D (4 registers), A (2 for .16816 u8 / 4 for .16832), B (1 / 2), C (4 or RZ): everything is data
+        na, nb = (4, 2) if ".16832" in op else (2, 1)
+        regs = [regs_in(t) for t in ops]
+        if regs and regs[0]:
+            dests += expand(regs[0][0], 4)
+        for t, n_ in zip(regs[1:], (na, nb, 4)):
+            if t:
+                srcs += expand(t[0], n_)
+        return dests, srcs, addr, data
     # generic ALU form: leading predicate dests, one register dest, optional carry-out predicates
     i = 0
     while i < len(ops) and is_plain_reg(ops[i]) and regs_in(ops[i]) and regs_in(ops[i])[0].lstrip("U").startswith("P"):
@@ -320,6 +332,7 @@ def audit(name, insns, secret_offsets, verbose=False):
     state = [None] * n          # dict name -> SEC / PTR
     state[0] = {}
     stack_secret = [False]
+    smem_secret = [False]
     violations = {}
     work = [0]
     inwork = {0}
@@ -408,8 +421,10 @@ def audit(name, insns, secret_offsets, verbose=False):
             bad = [r for r in addr + ([ins.guard] if ins.guard else []) if is_sec(rd(r))]
             if bad:
                 flag(ins, "secret-dependent memory address / predicate", bad)
-            if base in ("STS",) and is_sec(taint_of(data)):
-                flag(ins, "secret stored to shared memory", data)
+        if base == "SHFL" and len(ins.operands) >= 4:
+            bad = [r for r in regs_in(ins.operands[3]) if is_sec(rd(r))]         # the source-lane operand
+            if bad:
+                flag(ins, "secret-dependent shuffle lane", bad)
         if base in VARLAT_OPS and is_sec(taint_of(srcs)):
             flag(ins, "variable-latency instruction on secret data", srcs)
 
@@ -420,9 +435,17 @@ def audit(name, insns, secret_offsets, verbose=False):
         elif base == "LDL":
             new = SEC if stack_secret[0] else None
         elif base in ("LDS", "LDSM"):
-            new = None
+            new = SEC if smem_secret[0] else None
         elif base in ("LDC", "ULDC", "LDCU"):
             new = PTR if reads_secret_param else None
+        elif base in ("STS",):
+            if is_sec(taint_of(data)) and not smem_secret[0]:
+                smem_secret[0] = True
+                # shared memory became secret: re-run everything that loads from it
+                for j, other in enumerate(insns):
+                    if other.op.startswith("LDS") and state[j] is not None and j not in inwork:
+                        work.append(j)
+                        inwork.add(j)
         elif base in ("STL",):
             if is_sec(taint_of(data)) and not stack_secret[0]:
                 stack_secret[0] = True
@@ -531,7 +554,7 @@ def audit(name, insns, secret_offsets, verbose=False):
                 if is_sec(state[k0].get(r)):
                     explain(k0, r, 1)
     return {"kernel": name, "instructions": n, "secret_loads": secret_loads, "instructions_on_secret_data": tainted_instrs,
-            "stack_holds_secrets": stack_secret[0], "reached": sum(1 for s in state if s is not None),
+            "stack_holds_secrets": stack_secret[0], "shared_memory_holds_secrets": smem_secret[0], "reached": sum(1 for s in state if s is not None),
             "violations": [{"addr": hex(a), "kind": kind, "sass": text, "regs": regs} for (a, kind), (text, regs) in sorted(violations.items())]}
 
 

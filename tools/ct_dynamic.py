@@ -44,9 +44,11 @@ def run(n=16384, workdir=None):
     assert all([k for k, _ in caps[c]] == names for c in caps), "different kernel sequences"
     out = {"operations_per_launch": n, "metrics": METRICS, "classes": list(caps), "launches": [], "identical": True,
            "how": "every counter must be identical for all-zero, all-one and random secrets.  One exception, reported per launch as 'noisy': the "
-                  "shared-memory WAVEFRONT counter of the ragged kernels (k_sign_nonce<1>, k_sign_finish<1>), whose only shared-memory traffic is "
-                  "the bitonic sort of the PUBLIC message lengths: it includes arbitration replays and differs by ~1e-4 between two runs on "
-                  "identical inputs (shared-memory instruction counts are exact); there the criterion is a relative spread below 2e-3"}
+                  "shared-memory WAVEFRONT counter (l1tex__data_pipe_lsu_wavefronts_mem_shared).  It includes replays caused by arbitration with the "
+                  "kernel's local-memory traffic in the same L1 pipeline and is not reproducible: it differs by ~5e-5 between launches on IDENTICAL "
+                  "inputs (e.g. three k_comb<0> launches with all-zero secrets: 579576 / 579570 / 579629) in no consistent order of the classes.  "
+                  "For that one counter the criterion is a relative spread below 1e-3; the shared-memory load / store INSTRUCTION counts, which "
+                  "secret-dependent predication would change, are exact like everything else"}
     for i, name in enumerate(names):
         row = {"kernel": name, "counters": {}, "identical": True, "noisy": []}
         for m in METRICS:
@@ -55,7 +57,7 @@ def run(n=16384, workdir=None):
                 row["counters"][m] = vals[0]
                 continue
             row["counters"][m] = dict(zip(caps, vals))
-            if m == SHARED_WAVEFRONTS and "<1>" in name and max(vals) - min(vals) <= 2e-3 * max(vals):
+            if m == SHARED_WAVEFRONTS and max(vals) - min(vals) <= 1e-3 * max(vals):
                 row["noisy"].append(m)
             else:
                 row["identical"] = False
