@@ -51,7 +51,7 @@ PROD_M, PROD_S = 72, 44              # wide multiplies per field multiplication 
 # field operations per op: reference counts (instrumented reference) and the counts
 # this engine executes (tests/test_host_sim.py::test_field_op_counts pins them)
 REF_FM = {"verify": (2291, 1514), "sign": (506, 254), "genpub": (506, 254), "x25519_base": (505, 254), "x25519": (1292, 1278)}
-OURS_FM_SINGLE = {"sign": (369, 254), "genpub": (369, 254), "x25519_base": (368, 254), "x25519": (1283, 1272)}   # 51-row signed radix-32 comb
+OURS_FM_SINGLE = {"sign": (313, 254), "genpub": (313, 254), "x25519_base": (312, 254), "x25519": (1283, 1272)}   # 43-row signed radix-64 comb
 # the kernels share one inversion (254 S + 11 M) among up to EDG_BATCH = 32 operations of a thread, +3 M per operation;
 # a thread of the persistent grid gets n / (resident threads) operations, so at 2^20 per GPU the share is 14..28
 EDG_BATCH = 32

@@ -212,11 +212,11 @@ def verify_tables():
 
 def comb_table():
     """Diagnostic: the device-built fixed-base comb table as a (rows, entries, 96) uint8 array."""
-    buf = np.empty(1 << 20, np.uint8)
+    buf = np.empty(1 << 21, np.uint8)
     got = lib().eddsa_b200_comb_table(_p(buf), buf.nbytes)
     if got == 0 or got % 96:
         raise EddsaB200Error(f"eddsa_b200_comb_table returned {got}: " + lib().eddsa_b200_last_error().decode(errors="replace"))
-    shape = {51 * 16: (51, 16), 64 * 8: (64, 8)}[got // 96]                      # comb window W = 5 / W = 4 (sc.cuh: EDG_COMB_W)
+    shape = {43 * 32: (43, 32), 51 * 16: (51, 16), 64 * 8: (64, 8)}[got // 96]   # comb window W = 6 / 5 / 4 (sc.cuh: EDG_COMB_W)
     return buf[:got].reshape(shape + (96,)).copy()
 
 

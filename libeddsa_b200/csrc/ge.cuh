@@ -184,41 +184,64 @@ EDG_HD void ge_pre_select_ct(ge_pre &t, const u32 *row, int digit) {
 
 #define EDG_XCHG_STRIDE 28     /* words per lane in a warp's exchange area of ge_pre_select_mma (16-byte aligned, conflict-free reads) */
 #if defined(__CUDA_ARCH__)
-// The same constant-time lookup as ONE-HOT x TABLE contraction on the tensor cores (device only, warp-synchronous: all 32
-// lanes must call).  Scanning 16 entries x 24 words with masks costs 384 LOP3 + 96 LDS.128 per lookup — half of the ALU
-// work of a fixed-base operation, and the comb kernel is held back by exactly that (multiplier pipe 59 % busy, ALU pipe
-// 46 %).  Here lane L contributes the one-hot row [|digit_L| == k + 1], k = 0..15, of a 32 x 16 matrix A (u8), the table row is
-// a 16 x 96 matrix B of bytes, and D = A B (s32, exact: one byte per sum) holds the selected entry of every lane:
-// 24 x mma.sync.m16n8k16.u8.u8 per warp.  Still constant time: every entry takes part in every product, and no address
-// or branch depends on a digit (the digits only ever travel as DATA: shuffles, mma operands, shared-memory stores at
-// lane-indexed addresses).
-//   row_mma : this row in fragment order (built by k_comb_layout): word [nt * 32 + lane] = bytes of entries 4q .. 4q+3
-//             (q = lane % 4) at column lane / 4 of byte-tile nt; column (nt = 2m + s, n = 2q' + b) is entry byte
-//             4 (6 q' + m) + 2 s + b, chosen so that a thread's results of two neighbouring tiles form one complete word
-//   xchg    : this warp's exchange area in shared memory, 32 lanes x EDG_XCHG_STRIDE words (results come out spread over
-//             the four threads of a quad and are handed to their lane through it)
+// The same constant-time lookup as a ONE-HOT x TABLE contraction on the tensor cores (device only, warp-synchronous: all
+// 32 lanes must call).  Scanning ENTRIES x 24 words with masks costs ENTRIES x (24 LOP3 + 6 LDS.128) per lookup — with 16
+// entries half of the ALU work of a fixed-base operation, and the comb kernel was held back by exactly that (multiplier
+// pipe 59 % busy, ALU pipe 46 %).  Here lane L contributes the one-hot row [|digit_L| == k + 1], k = 0 .. ENTRIES - 1, of a
+// 32 x ENTRIES matrix A (u8), the table row is an ENTRIES x 96 matrix B of bytes, and D = A B (s32, exact: one byte per
+// sum) holds the selected entry of every lane: 24 x mma.sync.m16n8k16 (16 entries) / m16n8k32 (32 entries) per warp,
+// whatever the row length — which is what makes the 32-entry rows of the radix-64 comb affordable.
+// Still constant time: every entry takes part in every product, and no address or branch depends on a digit (the digits
+// only ever travel as DATA: shuffles, mma operands, shared-memory stores at lane-indexed addresses).
+//   row_mma : this row in fragment order (built by k_comb_layout): word [(nt * H + h) * 32 + lane], H = ENTRIES / 16,
+//             = bytes of entries 16h + 4q .. 16h + 4q + 3 (q = lane % 4) at column lane / 4 of byte-tile nt; column
+//             (nt = 2m + s, n = 2q' + b) is entry byte 4 (6 q' + m) + 2 s + b, chosen so that a thread's results of two
+//             neighbouring tiles form one complete word
+//   xchg    : this warp's exchange area in shared memory, 32 lanes x EDG_XCHG_STRIDE words (results come out spread
+//             over the four threads of a quad and are handed to their lane through it)
+// (Measured and rejected: issuing the lookup of digit j + 1 before the point addition of digit j, through a second exchange
+// area, so that the tensor-core latency and the packing overlap the addition: genpub 219.8 -> 217.5 M/s.)
+template <int H>       // one-hot bytes k = 16h + 4q .. + 3 (h < H) of lane `absd`'s row, as H words
+__device__ __forceinline__ void ge_onehot_words(u32 *a, u32 absd, u32 q) {
+#pragma unroll
+    for (int h = 0; h < H; h++) {
+        const u32 x = absd - 1u - 16u * h - 4u * q;                     // 0..3 iff the entry is one of these four
+        const u32 hit = 0u - ((((x >> 2) - 1u) >> 31));                    // all-ones iff x < 4
+        a[h] = (1u << ((x & 3u) * 8u)) & hit;
+    }
+}
+
+template <int H>
+__device__ __forceinline__ void ge_mma_u8(int d[4], const u32 *a_lo, const u32 *a_hi, const u32 *b) {
+    if constexpr (H == 1)
+        asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a_lo[0]), "r"(a_hi[0]), "r"(b[0]), "r"(0));
+    else   // k32: registers (row g, k < 16), (row g + 8, k < 16), (row g, k >= 16), (row g + 8, k >= 16)
+        asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+            : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a_lo[0]), "r"(a_hi[0]), "r"(a_lo[H - 1]), "r"(a_hi[H - 1]), "r"(b[0]), "r"(b[H - 1]), "r"(0));
+}
+
+template <int ENTRIES>
 __device__ __forceinline__ void ge_pre_select_mma(ge_pre &t, const u32 *row_mma, int digit, u32 *xchg) {
+    static_assert(ENTRIES == 16 || ENTRIES == 32, "one m16n8k16 or m16n8k32 product per byte-tile");
+    constexpr int H = ENTRIES / 16;
     const u32 lane = threadIdx.x & 31u, g = lane >> 2, q = lane & 3u;
     const u32 neg = ct_mask((u32)(digit >> 31));         // all-ones if digit < 0
-    const u32 absd = ((u32)digit ^ neg) - neg;           // 0 .. 16
-    u32 a[4];                                            // one-hot bytes k = 4q .. 4q+3 of rows (lanes) g, g+8, g+16, g+24
+    const u32 absd = ((u32)digit ^ neg) - neg;           // 0 .. ENTRIES
+    u32 a[4][H];                                         // one-hot bytes of rows (lanes) g, g+8, g+16, g+24
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const u32 x = __shfl_sync(0xffffffffu, absd, (int)(g + 8u * r)) - 1u - 4u * q;     // 0..3 iff that lane's entry is one of ours
-        const u32 hit = 0u - ((((x >> 2) - 1u) >> 31));                                       // all-ones iff x < 4
-        a[r] = (1u << ((x & 3u) * 8u)) & hit;
-    }
+    for (int r = 0; r < 4; r++) ge_onehot_words<H>(a[r], __shfl_sync(0xffffffffu, absd, (int)(g + 8u * r)), q);
     __syncwarp();                                        // the previous lookup's results have been read by every lane
 #pragma unroll
     for (int m = 0; m < 6; m++) {
-        const u32 b0 = row_mma[(2 * m) * 32 + lane], b1 = row_mma[(2 * m + 1) * 32 + lane];
+        u32 b0[H], b1[H];
+#pragma unroll
+        for (int h = 0; h < H; h++) { b0[h] = row_mma[((2 * m) * H + h) * 32 + lane]; b1[h] = row_mma[((2 * m + 1) * H + h) * 32 + lane]; }
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
             int d0[4], d1[4];
-            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
-                : "=r"(d0[0]), "=r"(d0[1]), "=r"(d0[2]), "=r"(d0[3]) : "r"(a[2 * mt]), "r"(a[2 * mt + 1]), "r"(b0), "r"(0));
-            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
-                : "=r"(d1[0]), "=r"(d1[1]), "=r"(d1[2]), "=r"(d1[3]) : "r"(a[2 * mt]), "r"(a[2 * mt + 1]), "r"(b1), "r"(0));
+            ge_mma_u8<H>(d0, a[2 * mt], a[2 * mt + 1], b0);
+            ge_mma_u8<H>(d1, a[2 * mt], a[2 * mt + 1], b1);
             // (c0, c1): row g + 16 mt, (c2, c3): row g + 8 + 16 mt; columns 2q, 2q+1 -> word 6q + m of that lane's entry
             const u32 lo = __byte_perm(__byte_perm((u32)d0[0], (u32)d0[1], 0x0040), __byte_perm((u32)d1[0], (u32)d1[1], 0x0040), 0x5410);
             const u32 hi = __byte_perm(__byte_perm((u32)d0[2], (u32)d0[3], 0x0040), __byte_perm((u32)d1[2], (u32)d1[3], 0x0040), 0x5410);

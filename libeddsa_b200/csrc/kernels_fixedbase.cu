@@ -18,8 +18,8 @@ using namespace edg;
 #define EDG_COMB_THREADS 512
 #endif
 #ifndef EDG_COMB_BLOCKS
-#define EDG_COMB_BLOCKS 1        /* resident blocks per SM: 512 threads x 128 registers = 4 warps per scheduler, one 78 KB copy of the
-                                    table per SM (2 x 256 threads: -2 %; 128 x 4 with the radix-16 table: -13 %) */
+#define EDG_COMB_BLOCKS 1        /* resident blocks per SM: 512 threads x 128 registers = 4 warps per scheduler, one copy of the table
+                                    (132 KB) + 16 exchange areas (56 KB) per SM (2 x 256 threads: -2 %) */
 #endif
 #ifndef EDG_FIXEDBASE_PASS_LOG2
 #define EDG_FIXEDBASE_PASS_LOG2 21   /* operations per pass of the staged kernels: bounds the scratch (64 B per signature) */
@@ -28,8 +28,11 @@ using namespace edg;
 #define EDG_MSG_TILE 512         /* ragged batches: consecutive operations sorted by message length together (4 per thread: small
                                     tiles keep enough blocks in flight — a verify pass of 303 104 signatures is 592 tiles) */
 #endif
+#ifndef EDG_LB_HASH
+#define EDG_LB_HASH 4            /* hash kernels: min resident blocks per SM the register allocator must allow */
+#endif
 #ifndef EDG_COMB_MMA
-#define EDG_COMB_MMA (EDG_COMB_W == 5)   /* table lookups as one-hot x table products on the tensor cores (ge.cuh) */
+#define EDG_COMB_MMA (EDG_COMB_W >= 5)   /* table lookups as one-hot x table products on the tensor cores (ge.cuh) */
 #endif
 namespace {
 
@@ -124,16 +127,17 @@ __global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n
     }
 }
 
-// comb table in fragment order for ge_pre_select_mma: word [row][nt][lane] = bytes of entries 4q .. 4q+3 (q = lane % 4) at
-// entry byte 4 (6 (g / 2) + nt / 2) + 2 (nt % 2) + g % 2, g = lane / 4
+// comb table in fragment order for ge_pre_select_mma: word [row][(nt * H + h) * 32 + lane] = bytes of entries
+// 16h + 4q .. 16h + 4q + 3 (q = lane % 4) at entry byte 4 (6 (g / 2) + nt / 2) + 2 (nt % 2) + g % 2, g = lane / 4
 __global__ void k_comb_layout(u32 *mma, const u32 *table) {
+    constexpr unsigned H = EDG_COMB_ENTRIES / 16 ? EDG_COMB_ENTRIES / 16 : 1;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= EDG_COMB_WORDS) return;
-    const unsigned row = idx / (EDG_COMB_ENTRIES * 24), rem = idx % (EDG_COMB_ENTRIES * 24), nt = rem / 32, lane = rem % 32;
+    const unsigned row = idx / (EDG_COMB_ENTRIES * 24), rem = idx % (EDG_COMB_ENTRIES * 24), nt = rem / (32 * H), h = rem / 32 % H, lane = rem % 32;
     const unsigned g = lane >> 2, q = lane & 3, byte = 4 * (6 * (g / 2) + nt / 2) + 2 * (nt % 2) + g % 2;
     u32 w = 0;
     for (unsigned i = 0; i < 4; i++) {
-        const u32 *entry = table + ((size_t)row * EDG_COMB_ENTRIES + 4 * q + i) * 24;
+        const u32 *entry = table + ((size_t)row * EDG_COMB_ENTRIES + 16 * h + 4 * q + i) * 24;
         w |= ((entry[byte >> 2] >> (8 * (byte & 3))) & 0xffu) << (8 * i);
     }
     mma[idx] = w;
@@ -173,7 +177,7 @@ __device__ __forceinline__ void for_each_message(size_t n, const unsigned long l
 
 // sign, stage 1: a[i] (as k_expand_key) and the nonce r[i] = H(prefix || M) mod L                  [ed25519-sha512.c:96-105]
 template <bool RAGGED>
-__global__ void __launch_bounds__(kThreads) k_sign_nonce(size_t n, u32 *a_out, u32 *r_out, const uint8_t *sec, const uint8_t *msgs,
+__global__ void __launch_bounds__(kThreads, EDG_LB_HASH) k_sign_nonce(size_t n, u32 *a_out, u32 *r_out, const uint8_t *sec, const uint8_t *msgs,
                                                          const unsigned long long *off, unsigned long long fixed_len) {
     for_each_message<RAGGED>(n, off, [&](size_t i) {
         const uint8_t *m; u64 len;
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(kThreads) k_sign_nonce(size_t n, u32 *a_out, u
 
 // sign, stage 3: S = r + H(R || pub || M) a mod L next to the R bytes k_comb wrote into sig[i]; wipes a[i], r[i].  [:112-122]
 template <bool RAGGED>
-__global__ void __launch_bounds__(kThreads) k_sign_finish(size_t n, uint8_t *sig, u32 *a_in, u32 *r_in, const uint8_t *pub, const uint8_t *msgs,
+__global__ void __launch_bounds__(kThreads, EDG_LB_HASH) k_sign_finish(size_t n, uint8_t *sig, u32 *a_in, u32 *r_in, const uint8_t *pub, const uint8_t *msgs,
                                                           const unsigned long long *off, unsigned long long fixed_len) {
     for_each_message<RAGGED>(n, off, [&](size_t i) {
         const uint8_t *m; u64 len;

@@ -139,20 +139,13 @@ EDG_HD void x25519_op(u32 out[8], const u32 scalar[8], const u32 point[8]) {
 // precomputed form, built once per device (comb_table_row below) and staged in shared memory by the kernels.
 // ------------------------------------------------------------------------------------------------
 EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
-    u32 e[8];
+    u32 e[EDG_COMB_EW];
     sc_recode_comb(e, x);
     ge_identity(r);
-    auto next_digit = [&e]() -> int {
-        const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
-#pragma unroll
-        for (int i = 0; i < 7; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
-        e[7] >>= EDG_COMB_W;
-        return digit;
-    };
 #pragma unroll 1
     for (int j = 0; j < EDG_COMB_ROWS; j++) {
         ge_pre t;
-        ge_pre_select_ct<EDG_COMB_ENTRIES>(t, comb + j * (EDG_COMB_ENTRIES * 24), next_digit());
+        ge_pre_select_ct<EDG_COMB_ENTRIES>(t, comb + j * (EDG_COMB_ENTRIES * 24), sc_comb_next_digit(e));
         ge_madd(r, r, t, j + 1 < EDG_COMB_ROWS);              // (public loop position) the last addition needs no T
     }
 }
@@ -161,18 +154,13 @@ EDG_HD void ge_scalarmult_base_ct(ge_p3 &r, const u32 x[8], const u32 *comb) {
 // The kernels' form: the same comb with the table lookups on the tensor cores (ge.cuh: ge_pre_select_mma).  Warp-
 // synchronous: all 32 lanes of the warp must be here.  comb_mma: the table in fragment order (EDG_COMB_WORDS words).
 __device__ __forceinline__ void ge_scalarmult_base_ct_mma(ge_p3 &r, const u32 x[8], const u32 *comb_mma, u32 *xchg) {
-    static_assert(EDG_COMB_ENTRIES == 16, "the tensor-core lookup is written for the 16-entry rows of the radix-32 comb");
-    u32 e[8];
+    u32 e[EDG_COMB_EW];
     sc_recode_comb(e, x);
     ge_identity(r);
 #pragma unroll 1
     for (int j = 0; j < EDG_COMB_ROWS; j++) {
-        const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
-#pragma unroll
-        for (int i = 0; i < 7; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
-        e[7] >>= EDG_COMB_W;
         ge_pre t;
-        ge_pre_select_mma(t, comb_mma + j * (EDG_COMB_ENTRIES * 24), digit, xchg);
+        ge_pre_select_mma<EDG_COMB_ENTRIES>(t, comb_mma + j * (EDG_COMB_ENTRIES * 24), sc_comb_next_digit(e), xchg);
         ge_madd(r, r, t, j + 1 < EDG_COMB_ROWS);
     }
 }

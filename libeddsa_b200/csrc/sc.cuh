@@ -108,13 +108,16 @@ EDG_HD void sc_muladd(u32 r[8], const u32 a[8], const u32 b[8], const u32 c[8]) 
 }
 
 // Fixed-base comb geometry: signed radix-2^W digits, one table row per digit (no doublings), 2^(W-1) entries per row.
-//   W = 4: 64 rows x  8 entries = 49 152 bytes     W = 5: 51 rows x 16 entries = 78 336 bytes (20 % fewer additions)
+//   W = 4: 64 rows x  8 entries = 49 152 bytes     W = 5: 51 rows x 16 entries = 78 336 bytes
+//   W = 6: 43 rows x 32 entries = 132 096 bytes (shipped: 33 % fewer additions than W = 4; needs the tensor-core lookup of
+//          ge.cuh — a masked scan of 32 entries would cost more than the additions it saves)
 #ifndef EDG_COMB_W
-#define EDG_COMB_W 5
+#define EDG_COMB_W 6
 #endif
 #define EDG_COMB_ROWS ((255 + EDG_COMB_W - 1) / EDG_COMB_W)
 #define EDG_COMB_ENTRIES (1 << (EDG_COMB_W - 1))
 #define EDG_COMB_WORDS (EDG_COMB_ROWS * EDG_COMB_ENTRIES * 24)
+#define EDG_COMB_EW ((EDG_COMB_W * EDG_COMB_ROWS + 31) / 32)     /* words of a recoded scalar (W = 6: 258 bits) */
 
 // word i of the recoding offset  2^(W-1) * sum_{j < ROWS} 2^(W j)
 EDG_HD constexpr u32 sc_comb_offset_word(int i) {
@@ -126,18 +129,26 @@ EDG_HD constexpr u32 sc_comb_offset_word(int i) {
     return w;
 }
 
-// Signed radix-2^W digits of x in [0, L): e = x + offset (no overflow: x < 2^253 and offset < 2^255 (W = 5) or
-// < 0.54 * 2^256 (W = 4)), then digit_j = ((e >> W j) mod 2^W) - 2^(W-1) in [-2^(W-1), 2^(W-1)) and
-// sum digit_j 2^(W j) = x.  Returned packed; callers shift W bits out per step.
-//                                                      [reference: con_off trick, sc.c:40 + ed.c:406-422]
-EDG_HD void sc_recode_comb(u32 e[8], const u32 x[8]) {
+// Signed radix-2^W digits of x in [0, L): e = x + offset (EDG_COMB_EW words; x < 2^253, offset < 2^(W ROWS)), then
+// digit_j = ((e >> W j) mod 2^W) - 2^(W-1) in [-2^(W-1), 2^(W-1)) and sum digit_j 2^(W j) = x.  Returned packed; callers
+// shift W bits out per step (sc_comb_next_digit).           [reference: con_off trick, sc.c:40 + ed.c:406-422]
+EDG_HD void sc_recode_comb(u32 e[EDG_COMB_EW], const u32 x[8]) {
     u32 carry = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const u64 t = (u64)x[i] + sc_comb_offset_word(i) + carry;
+    for (int i = 0; i < EDG_COMB_EW; i++) {
+        const u64 t = (u64)(i < 8 ? x[i] : 0u) + sc_comb_offset_word(i) + carry;
         e[i] = (u32)t;
         carry = (u32)(t >> 32);
     }
+}
+
+// the lowest digit of e, which is then shifted out (the position is public, the value is not)
+EDG_HD int sc_comb_next_digit(u32 e[EDG_COMB_EW]) {
+    const int digit = (int)(e[0] & ((1u << EDG_COMB_W) - 1u)) - (1 << (EDG_COMB_W - 1));
+#pragma unroll
+    for (int i = 0; i + 1 < EDG_COMB_EW; i++) e[i] = (e[i] >> EDG_COMB_W) | (e[i + 1] << (32 - EDG_COMB_W));
+    e[EDG_COMB_EW - 1] >>= EDG_COMB_W;
+    return digit;
 }
 
 }  // namespace edg

@@ -23,7 +23,7 @@ extern "C" {
 void h_sc_reduce512(uint32_t *r, const uint32_t *x) { sc_reduce512(r, x); }
 void h_sc_reduce256(uint32_t *r, const uint32_t *x) { sc_reduce256(r, x); }
 void h_sc_muladd(uint32_t *r, const uint32_t *a, const uint32_t *b, const uint32_t *c) { sc_muladd(r, a, b, c); }
-void h_sc_recode(uint32_t *e, const uint32_t *x) { sc_recode_comb(e, x); }
+void h_sc_recode(uint32_t *e, const uint32_t *x) { uint32_t t[EDG_COMB_EW]; sc_recode_comb(t, x); for (int i = 0; i < 9; i++) e[i] = i < EDG_COMB_EW ? t[i] : 0; }
 int h_comb_w(void) { return EDG_COMB_W; }
 }
 #include "../../libeddsa_b200/csrc/sha512.cuh"
