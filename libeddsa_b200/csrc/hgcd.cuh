@@ -15,9 +15,14 @@
 // second window table for 2^128 B).  This is the "TODO: batch verify"-free way to halve the work: every
 // signature is still decided on its own, exactly.
 //
-// If the Euclidean vector has an even rho the next vector of the sequence (always odd then) is used;
-// in the (never observed, ~2^-30) case that it would not fit, (rho, tau) = (1, t) — the plain
-// full-length computation — is the fallback, so the result never depends on luck.
+// If the Euclidean vector has an even rho the next vector of the sequence (always odd then) is used.  That vector can be
+// long: the fallback (rho, tau) = (1, t) — the plain full-length computation, ~1.7x the work — is taken exactly when the
+// short vector has an even rho AND its remainder is below 2^96 (the next cofactor could then exceed 160 bits).  For
+// uniformly random t (what a SHA-512 challenge is) that needs a partial quotient above 2^32 at the crossing of 2^128: probability
+// ~2^-33 per signature, never seen in 3 x 10^5 random challenges (tests/test_host_sim.py::test_half_gcd).  For STRUCTURED t
+// (small multiples or neighbours of L / 2^k, inverses of small numbers mod 8L ...) it is common — 28 % of a structured
+// fuzz set — but t is a hash output, so nobody can steer a signature there; either way the result never depends on luck:
+// the fallback decides the same equation.  The records of such signatures sort to the front of a pass (64 windows).
 #pragma once
 #include "fe.cuh"
 

@@ -11,5 +11,7 @@ for n in (1, 33, 700):
     pub = ed.ed25519_genpub_batch(sec)
     sig = ed.ed25519_sign_batch(sec, pub, blob, off=off)
     ok = ed.ed25519_verify_batch(sig, pub, blob, off=off); assert ok.all()
+    fixed = np.frombuffer(rng.bytes(n * 64), np.uint8)
+    sig2 = ed.ed25519_sign_batch(sec, pub, fixed, fixed_len=64); assert ed.ed25519_verify_batch(sig2, pub, fixed, fixed_len=64).all()
     ed.x25519_batch(sec, pts); ed.x25519_base_batch(sec); ed.pk_ed25519_to_x25519_batch(pub); ed.sk_ed25519_to_x25519_batch(sec)
 print("sanitize driver ok")
