@@ -314,6 +314,88 @@ out:
     return rc;
 }
 
+/* ---- staging copies: callers with ordinary (pageable) memory are bound by one thread's memcpy (~15 GB/s) long before the
+ * link (55 GB/s) when messages are large, so big copies into the pinned slots are split over a few helper threads.  One
+ * request at a time; a caller that finds the helpers busy (several devices staging at once) copies by itself. ---- */
+#define EDG_COPY_HELPERS 3
+#define EDG_COPY_PARALLEL_MIN ((size_t)8 << 20)
+static struct {
+    pthread_mutex_t busy, m;
+    pthread_cond_t go, done;
+    pthread_t th[EDG_COPY_HELPERS];
+    int started, stop, pending;
+    unsigned long gen;
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t slice, bytes;
+} g_copy = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, 0, 0, 0, NULL, NULL, 0, 0};
+
+static void *copy_helper(void *arg)
+{
+    const size_t k = (size_t)(uintptr_t)arg;           /* helper k copies slice k + 1 (the caller takes slice 0) */
+    unsigned long seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&g_copy.m);
+        while (g_copy.gen == seen && !g_copy.stop) pthread_cond_wait(&g_copy.go, &g_copy.m);
+        if (g_copy.stop) { pthread_mutex_unlock(&g_copy.m); return NULL; }
+        seen = g_copy.gen;
+        uint8_t *dst = g_copy.dst;
+        const uint8_t *src = g_copy.src;
+        const size_t lo = (k + 1) * g_copy.slice, hi = lo + g_copy.slice < g_copy.bytes ? lo + g_copy.slice : g_copy.bytes;
+        pthread_mutex_unlock(&g_copy.m);
+        if (lo < hi) memcpy(dst + lo, src + lo, hi - lo);
+        pthread_mutex_lock(&g_copy.m);
+        if (--g_copy.pending == 0) pthread_cond_signal(&g_copy.done);
+        pthread_mutex_unlock(&g_copy.m);
+    }
+}
+
+static void stage_copy(uint8_t *dst, const uint8_t *src, size_t bytes)
+{
+    size_t k;
+    if (bytes < EDG_COPY_PARALLEL_MIN || pthread_mutex_trylock(&g_copy.busy) != 0) { memcpy(dst, src, bytes); return; }
+    pthread_mutex_lock(&g_copy.m);
+    if (!g_copy.started) {
+        g_copy.started = 1;
+        for (k = 0; k < EDG_COPY_HELPERS; k++)
+            if (pthread_create(&g_copy.th[k], NULL, copy_helper, (void *)(uintptr_t)k) != 0) { g_copy.started = -1; break; }
+    }
+    if (g_copy.started < 0) {                           /* no helpers: plain copy */
+        pthread_mutex_unlock(&g_copy.m);
+        pthread_mutex_unlock(&g_copy.busy);
+        memcpy(dst, src, bytes);
+        return;
+    }
+    g_copy.dst = dst; g_copy.src = src; g_copy.bytes = bytes;
+    g_copy.slice = ((bytes + EDG_COPY_HELPERS) / (EDG_COPY_HELPERS + 1) + 4095) & ~(size_t)4095;
+    g_copy.pending = EDG_COPY_HELPERS;
+    g_copy.gen++;
+    pthread_cond_broadcast(&g_copy.go);
+    pthread_mutex_unlock(&g_copy.m);
+    memcpy(dst, src, g_copy.slice < bytes ? g_copy.slice : bytes);
+    pthread_mutex_lock(&g_copy.m);
+    while (g_copy.pending > 0) pthread_cond_wait(&g_copy.done, &g_copy.m);
+    pthread_mutex_unlock(&g_copy.m);
+    pthread_mutex_unlock(&g_copy.busy);
+}
+
+static void copy_pool_stop(void)
+{
+    size_t k;
+    pthread_mutex_lock(&g_copy.busy);
+    pthread_mutex_lock(&g_copy.m);
+    if (g_copy.started > 0) {
+        g_copy.stop = 1;
+        pthread_cond_broadcast(&g_copy.go);
+        pthread_mutex_unlock(&g_copy.m);
+        for (k = 0; k < EDG_COPY_HELPERS; k++) pthread_join(g_copy.th[k], NULL);
+        pthread_mutex_lock(&g_copy.m);
+        g_copy.started = 0; g_copy.stop = 0;
+    }
+    pthread_mutex_unlock(&g_copy.m);
+    pthread_mutex_unlock(&g_copy.busy);
+}
+
 static size_t msg_bytes(const edg_job_t *j, size_t lo, size_t hi)
 {
     if (!j->has_msgs) return 0;
@@ -341,7 +423,7 @@ static void retire_slot(edg_dev_t *c, const edg_job_t *j, slot_t *sl, int s, int
 {
     const size_t m = sl->hi - sl->lo;
     if (!pin_out) {
-        if (copy_out) memcpy(j->out + sl->lo * j->out_item, c->h_out[s], m * j->out_item);
+        if (copy_out) stage_copy(j->out + sl->lo * j->out_item, c->h_out[s], m * j->out_item);
         if (op_secret_out(j->op) && !g_no_scrub) memset(c->h_out[s], 0, m * j->out_item);
     }
     if (sl->staged_secret && !g_no_scrub) memset(c->h_in[s], 0, m * j->in_item[0]);
@@ -352,7 +434,8 @@ static void retire_slot(edg_dev_t *c, const edg_job_t *j, slot_t *sl, int s, int
 static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
 {
     int rc = 0, k, s, prev_dev = -1;
-    size_t pos, nshard = hi - lo, target;
+    size_t pos, nshard = hi - lo, target, wave;
+    int staged = 0;
     slot_t slot[EDG_NSLOT];
     int pin_in[3] = {0, 0, 0}, pin_msgs = 0, pin_out = 0;
     size_t chunk_no = 0;
@@ -372,13 +455,25 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
      * stream so that the stages never share an SM (instruction cache) while copies overlap on the slot streams */
     if (j->op == OP_VERIFY && nshard > c->verify_pass) target = c->verify_pass;
     if (target > nshard) target = nshard;
+    /* the first chunk's staging and copy are exposed, so chunks start small and grow: verify one wave first (then, when
+     * the inputs have to be staged through the pinned slots — a memcpy the GPU waits for — 1, 2 waves), the other
+     * operations 65536 items and four times more each chunk */
+    for (k = 0; k < j->nin; k++) staged |= !pin_in[k];
+    staged |= j->has_msgs && !pin_msgs;
+    wave = j->op == OP_VERIFY && target == c->verify_pass && c->verify_pass >= 8 ? c->verify_pass / edg_verify_waves() : 0;
     for (pos = lo; pos < hi;) {
         size_t m = target, in_bytes, out_bytes, ofs;
         uint8_t *d_in[3] = {NULL, NULL, NULL};
         const uint8_t *d_msgs = NULL;
         const unsigned long long *d_off = NULL;
-        /* verify: a short first chunk (one wave) so that the kernels start early; its copy is the only exposed one */
-        if (j->op == OP_VERIFY && chunk_no == 0 && target == c->verify_pass && c->verify_pass >= 8) m = c->verify_pass / edg_verify_waves();
+        if (wave) {
+            if (chunk_no == 0) m = wave;
+            else if (staged && chunk_no == 1) m = wave;
+            else if (staged && chunk_no == 2) m = 2 * wave;
+        } else if (staged && chunk_no < 4) {
+            m = (size_t)65536 << (2 * chunk_no);
+            if (m > target) m = target;
+        }
         if (pos + m > hi) m = hi - pos;
         /* shrink the chunk until it fits the staging budget (ragged messages); a single oversized item grows the buffers */
         while (m > 1 && chunk_in_bytes(j, pos, pos + m) > g_chunk_bytes) m = (m + 1) / 2;
@@ -405,7 +500,7 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
             size_t bytes = m * j->in_item[k];
             const uint8_t *src = j->in[k] + pos * j->in_item[k];
             if (!pin_in[k]) {
-                memcpy(c->h_in[s] + ofs, src, bytes);
+                stage_copy(c->h_in[s] + ofs, src, bytes);
                 src = c->h_in[s] + ofs;
                 if (k == 0 && secret_in) slot[s].staged_secret = 1;
             }
@@ -425,7 +520,7 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
                 ofs += align_up((m + 1) * sizeof *ho);
             }
             if (mb) {
-                if (!pin_msgs) { memcpy(c->h_in[s] + ofs, src, mb); src = c->h_in[s] + ofs; }
+                if (!pin_msgs) { stage_copy(c->h_in[s] + ofs, src, mb); src = c->h_in[s] + ofs; }
                 CU(cudaMemcpyAsync(c->d_in[s] + ofs, src, mb, cudaMemcpyHostToDevice, c->stream[s]));
             }
             d_msgs = c->d_in[s] + ofs;
@@ -777,6 +872,7 @@ void eddsa_b200_shutdown(void)
         edg_dev_t *c = &g_dev[d];
         if (!__atomic_load_n(&c->ready, __ATOMIC_ACQUIRE)) continue;
         worker_stop(c);
+        copy_pool_stop();
         pthread_mutex_lock(&g_ctx_lock);
         pthread_mutex_lock(&c->lock);
         cudaSetDevice(d);
