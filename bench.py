@@ -334,8 +334,14 @@ def run_ours(args):
     t0 = time.perf_counter()
     for _ in range(K):
         e2e_step()
+    own_s = time.perf_counter() - t0                             # this rank's own K steps (before waiting for the others)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    per_rank = [own_s]
+    if world > 1:
+        t_all = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(t_all, torch.tensor([own_s], dtype=torch.float64, device=dev))
+        per_rank = [float(t.item()) for t in t_all]
     assert bool(h_ok.all().item())
     e2e_value = world * n * K / e2e_s
     # ---- the same from ordinary (pageable) memory: the library stages through its pinned slots ------------------
@@ -449,7 +455,10 @@ def run_ours(args):
                        "batch_per_gpu": n, "global_batch": n * world, "msg_len": 64, "sharding": "by rank, no collective",
                        "l2": "inputs 168 MB > 126 MB L2 and a 256 MB flush write between timed steps"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * (64 + 32 + 64), "d2h_bytes_per_step": n,
-                    "api": "ed25519_verify_batch (host buffers, pinned)", "ms_per_step": e2e_s / K * 1e3},
+                    "api": "ed25519_verify_batch (host buffers, pinned)", "ms_per_step": e2e_s / K * 1e3,
+                    "ms_per_step_by_rank": [round(t / K * 1e3, 3) for t in per_rank],
+                    "note": "value = all ranks' signatures / the slowest rank's time; the ranks share one host (pinned buffers and PCIe "
+                            "paths on whichever NUMA node each process landed), so their own times differ — see ms_per_step_by_rank"},
             "gpu_launches": int(launches),
             "roofline": roofline, "cpu_baseline": cpu_b, "also": also, "clocks": clocks,
         }

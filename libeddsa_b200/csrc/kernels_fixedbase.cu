@@ -21,6 +21,9 @@ using namespace edg;
 #define EDG_COMB_BLOCKS 1        /* resident blocks per SM: 512 threads x 128 registers = 4 warps per scheduler, one copy of the table
                                     (132 KB) + 16 exchange areas (56 KB) per SM (2 x 256 threads: -2 %) */
 #endif
+#ifndef EDG_COMB_LB_THREADS
+#define EDG_COMB_LB_THREADS EDG_COMB_THREADS     /* register budget of k_comb = 65536 / this */
+#endif
 #ifndef EDG_FIXEDBASE_PASS_LOG2
 #define EDG_FIXEDBASE_PASS_LOG2 21   /* operations per pass of the staged kernels: bounds the scratch (64 B per signature) */
 #endif
@@ -66,7 +69,7 @@ __device__ __forceinline__ void wipe_words8(u32 *dst) {
 // MODE 1: out[i] = Montgomery u of (clamp(scalars[i]) mod L) * B for raw 32-byte scalars (x25519_base)
 // Every thread runs up to EDG_BATCH operations with one shared inversion (ops.cuh: fe_batch_inv).
 template <int MODE>
-__global__ void __launch_bounds__(kCombThreads, EDG_COMB_BLOCKS) k_comb(size_t n, uint8_t *out, unsigned out_stride, u32 *scalars, int wipe,
+__global__ void __launch_bounds__(EDG_COMB_LB_THREADS, EDG_COMB_BLOCKS) k_comb(size_t n, uint8_t *out, unsigned out_stride, u32 *scalars, int wipe,
                                                                       const u32 *__restrict__ comb_g) {
     extern __shared__ __align__(16) u32 s_comb[];                // the table | one exchange area per warp (EDG_COMB_MMA)
     stage_table(s_comb, comb_g, EDG_COMB_WORDS);
