@@ -24,6 +24,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include "eddsa.h"
 #include "eddsa_batch.h"
@@ -32,6 +33,7 @@
 #define EDG_MAX_DEV 16
 #define EDG_NSLOT 3
 #define EDG_ALIGN 256
+#define EDG_COPY_HELPERS 3              /* helper threads for big staging copies, at most; g_copy_helpers of them are used */
 
 typedef enum { OP_GENPUB, OP_SIGN, OP_VERIFY, OP_X25519, OP_X25519_BASE, OP_PK_CONV, OP_SK_CONV, OP_FE_TEST, OP_SC_TEST } edg_op_t;
 
@@ -82,6 +84,7 @@ typedef struct shard { edg_dev_t *c; const edg_job_t *j; size_t lo, hi; int rc; 
 static edg_dev_t g_dev[EDG_MAX_DEV]; /* indexed by CUDA device ordinal */
 static int g_list[EDG_MAX_DEV];      /* devices the host-buffer API shards over */
 static int g_nlist = 0, g_nactive = 0, g_init_rc = 0, g_no_scrub = 0;
+static int g_copy_helpers = 0;       /* helper threads for big staging copies (stage_copy): set once in global_init */
 static size_t g_chunk_bytes = (size_t)128 << 20;
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
 static pthread_mutex_t g_ctx_lock = PTHREAD_MUTEX_INITIALIZER;
@@ -142,6 +145,12 @@ static void global_init(void)
     if (env_int("EDDSA_B200_DEBUG_FULL_SCALARS", 0) > 0) edg_verify_debug_full_scalars(1);
     if (env_int("EDDSA_B200_VERIFY_WAVES", 0) > 0) edg_verify_set_waves(env_int("EDDSA_B200_VERIFY_WAVES", 0));
     g_no_scrub = env_int("EDDSA_B200_DEBUG_NO_SCRUB", 0) > 0;   /* test hook: negative control of the staging-scrub test */
+    /* helpers for big staging copies: a quarter of the host's cores per visible device, at most 3 — a host shared by one
+     * process per GPU (or by eight device workers of this process, which already copy in parallel) gets fewer or none */
+    g_copy_helpers = (int)(sysconf(_SC_NPROCESSORS_ONLN) / (4 * (long)count));
+    if (getenv("EDDSA_B200_COPY_THREADS")) g_copy_helpers = env_int("EDDSA_B200_COPY_THREADS", 0);
+    if (g_copy_helpers > EDG_COPY_HELPERS) g_copy_helpers = EDG_COPY_HELPERS;
+    if (g_copy_helpers < 0) g_copy_helpers = 0;
 }
 
 static int engine_ready(void)
@@ -317,7 +326,6 @@ out:
 /* ---- staging copies: callers with ordinary (pageable) memory are bound by one thread's memcpy (~15 GB/s) long before the
  * link (55 GB/s) when messages are large, so big copies into the pinned slots are split over a few helper threads.  One
  * request at a time; a caller that finds the helpers busy (several devices staging at once) copies by itself. ---- */
-#define EDG_COPY_HELPERS 3
 #define EDG_COPY_PARALLEL_MIN ((size_t)8 << 20)
 static struct {
     pthread_mutex_t busy, m;
@@ -353,11 +361,11 @@ static void *copy_helper(void *arg)
 static void stage_copy(uint8_t *dst, const uint8_t *src, size_t bytes)
 {
     size_t k;
-    if (bytes < EDG_COPY_PARALLEL_MIN || pthread_mutex_trylock(&g_copy.busy) != 0) { memcpy(dst, src, bytes); return; }
+    if (bytes < EDG_COPY_PARALLEL_MIN || g_copy_helpers < 1 || pthread_mutex_trylock(&g_copy.busy) != 0) { memcpy(dst, src, bytes); return; }
     pthread_mutex_lock(&g_copy.m);
     if (!g_copy.started) {
         g_copy.started = 1;
-        for (k = 0; k < EDG_COPY_HELPERS; k++)
+        for (k = 0; k < (size_t)g_copy_helpers; k++)
             if (pthread_create(&g_copy.th[k], NULL, copy_helper, (void *)(uintptr_t)k) != 0) { g_copy.started = -1; break; }
     }
     if (g_copy.started < 0) {                           /* no helpers: plain copy */
@@ -367,8 +375,8 @@ static void stage_copy(uint8_t *dst, const uint8_t *src, size_t bytes)
         return;
     }
     g_copy.dst = dst; g_copy.src = src; g_copy.bytes = bytes;
-    g_copy.slice = ((bytes + EDG_COPY_HELPERS) / (EDG_COPY_HELPERS + 1) + 4095) & ~(size_t)4095;
-    g_copy.pending = EDG_COPY_HELPERS;
+    g_copy.slice = ((bytes + g_copy_helpers) / ((size_t)g_copy_helpers + 1) + 4095) & ~(size_t)4095;
+    g_copy.pending = g_copy_helpers;
     g_copy.gen++;
     pthread_cond_broadcast(&g_copy.go);
     pthread_mutex_unlock(&g_copy.m);
@@ -388,7 +396,7 @@ static void copy_pool_stop(void)
         g_copy.stop = 1;
         pthread_cond_broadcast(&g_copy.go);
         pthread_mutex_unlock(&g_copy.m);
-        for (k = 0; k < EDG_COPY_HELPERS; k++) pthread_join(g_copy.th[k], NULL);
+        for (k = 0; k < (size_t)g_copy_helpers; k++) pthread_join(g_copy.th[k], NULL);
         pthread_mutex_lock(&g_copy.m);
         g_copy.started = 0; g_copy.stop = 0;
     }
