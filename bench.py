@@ -423,7 +423,7 @@ def run_ours(args):
         achieved = per_gpu * products(OURS_FM["verify"]) / 1e12
         roofline = {
             "bound": "int32-multiply (IMAD.WIDE on the fmaheavy pipe; compute-bound, see DESIGN.md §4)",
-            "kernel": "k_verify_scalars + k_verify_points + k_verify (one step = %d launches: the three stages per pass of 303 104 signatures)" % max(int(launches) // K, 1),
+            "kernel": "k_verify_scalars + k_verify_points + k_verify (one step = %d launches: three stages per pass of up to 1 212 416 signatures)" % max(int(launches) // K, 1),
             "achieved": achieved, "peak": PEAK_TMULS, "unit": "T wide-multiplies/s (32x32->64)", "frac": achieved / PEAK_TMULS,
             "frac_reference_fm": per_gpu * products(REF_FM["verify"]) / 1e12 / PEAK_TMULS,
             "peak_source": "measured: tools/pipe_bench.cu on this pool's B200 = 32 IMAD.WIDE/clk/SM x 148 SM x 1965 MHz (profiles/r01_pipe_microbench.md)",

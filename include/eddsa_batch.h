@@ -20,7 +20,7 @@
  * Device-buffer functions (…_batch_dev): all pointers are device pointers on the CURRENT CUDA device,
  * 16-byte aligned (the `ok` flags: any alignment); the work is enqueued on `stream` (a cudaStream_t,
  * NULL = default stream) and the call returns without synchronising.  Kernel scratch (verify: 2.4 KB
- * per signature of a pass of at most 303 104; sign / genpub: 64 / 32 bytes per operation of a pass
+ * per signature of a pass of at most 1 212 416; sign / genpub: 64 / 32 bytes per operation of a pass
  * of at most 2^21) is taken from a stream-ordered memory pool on `stream` and returned to it by the
  * same call, so any number of streams may be used and nothing synchronises.
  *

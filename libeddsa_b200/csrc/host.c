@@ -64,6 +64,7 @@ typedef struct {
     cudaStream_t kstream;                       /* verify: all kernels of the host-buffer pipeline run here, one after the other */
     cudaEvent_t in_ready[EDG_NSLOT], k_done[EDG_NSLOT];
     size_t verify_pass;                         /* signatures per full pass of the verify kernels (whole waves) */
+    size_t verify_wave, verify_chunk;           /* one wave of resident threads; chunk of the host-buffer pipeline (<= 4 waves) */
     uint8_t *h_in[EDG_NSLOT], *h_out[EDG_NSLOT];
     uint8_t *d_in[EDG_NSLOT], *d_out[EDG_NSLOT];
     size_t in_cap, out_cap;
@@ -206,6 +207,8 @@ static int dev_basic(int dev, edg_dev_t **out_ctx)
             }
             CU(cudaStreamCreateWithFlags(&c->kstream, cudaStreamNonBlocking));
             c->verify_pass = edg_verify_pass(sms);
+            c->verify_wave = c->verify_pass / edg_verify_waves();
+            c->verify_chunk = c->verify_wave * (edg_verify_waves() < 4 ? edg_verify_waves() : 4);   /* copies overlap kernels per chunk */
             /* scratch pool: freed blocks stay in the pool (no trimming at synchronisation points), so a steady
              * stream of calls allocates nothing after the first one */
             memset(&props, 0, sizeof props);
@@ -298,7 +301,7 @@ static int launch(edg_dev_t *c, edg_op_t op, size_t n, uint8_t *d_out, uint8_t *
     size_t need = 0, records = 0;
     unsigned launches = 0;
     if (n == 0) return 0;
-    if (op == OP_VERIFY) { records = n < c->verify_pass ? n : c->verify_pass; need = edg_verify_scratch_bytes(records); }
+    if (op == OP_VERIFY) { records = n < c->verify_pass ? n : c->verify_pass; need = edg_verify_scratch_bytes(records); }   /* 2.4 KB per signature */
     else if (op == OP_GENPUB || op == OP_SIGN) need = edg_fixedbase_scratch_bytes(op == OP_SIGN, n);
     if (need) CU(cudaMallocFromPoolAsync(&scratch, need, c->pool, (cudaStream_t)stream));
     switch (op) {
@@ -461,14 +464,14 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
     if (target < 65536) target = 65536;
     /* verify: chunks of whole passes of its kernels (whole waves of resident threads), kernels serialised on one
      * stream so that the stages never share an SM (instruction cache) while copies overlap on the slot streams */
-    if (j->op == OP_VERIFY && nshard > c->verify_pass) target = c->verify_pass;
+    if (j->op == OP_VERIFY && nshard > c->verify_chunk) target = c->verify_chunk;
     if (target > nshard) target = nshard;
     /* the first chunk's staging and copy are exposed, so chunks start small and grow: verify one wave first (then, when
      * the inputs have to be staged through the pinned slots — a memcpy the GPU waits for — 1, 2 waves), the other
      * operations 65536 items and four times more each chunk */
     for (k = 0; k < j->nin; k++) staged |= !pin_in[k];
     staged |= j->has_msgs && !pin_msgs;
-    wave = j->op == OP_VERIFY && target == c->verify_pass && c->verify_pass >= 8 ? c->verify_pass / edg_verify_waves() : 0;
+    wave = j->op == OP_VERIFY && target == c->verify_chunk && c->verify_wave >= 8 ? c->verify_wave : 0;
     for (pos = lo; pos < hi;) {
         size_t m = target, in_bytes, out_bytes, ofs;
         uint8_t *d_in[3] = {NULL, NULL, NULL};

@@ -354,10 +354,11 @@ def test_verify_full_length_fallback_path_on_the_device(cpu):
 
 
 def test_verify_pass_boundaries(ed, cpu):
-    """The two verify kernels work in passes of whole waves (303 104 signatures on 148 SMs) and hand records out in
-    sorted order: batches one past a pass, with a ragged last warp, through the device API (one launch pair per
-    pass) and the host pipeline (short first chunk), every tenth signature corrupted, compared with the oracle on a
-    sample and by position (the corrupted ones, and only they, are rejected)."""
+    """The verify kernels work in passes of whole waves of resident threads and visit the records in sorted order; the
+    host pipeline cuts a batch into chunks of four waves (303 104 signatures on 148 SMs) after a one-wave first chunk:
+    a batch one past a chunk, with a ragged last warp, through the device API and the host pipeline, every tenth
+    signature corrupted, compared with the oracle on a sample and by position (the corrupted ones, and only they, are
+    rejected).  (Several passes inside ONE device-API call: test_gpu_round2.py::test_verify_several_passes_per_call.)"""
     import torch
     rng = np.random.default_rng(650)
     n = 303_104 + 1 + 37

@@ -244,6 +244,39 @@ def test_many_user_streams(ed):
         assert torch.equal(sg, ref) and ok.all().item()
 
 
+def test_verify_several_passes_per_call():
+    """A device-API verify call of more signatures than one pass holds runs pass after pass over the same record slab
+    (by default a pass is 16 waves = 1.2 M signatures; EDDSA_B200_VERIFY_WAVES=1 makes it 75 776, so that a 200 000-
+    signature call is three passes with a ragged last one).  Fixed and ragged messages, corrupted rows rejected by
+    position, same decisions as the host pipeline.  Own process: the setting is read once at initialisation."""
+    code = r"""
+import os, sys, numpy as np, torch
+sys.path.insert(0, %r)
+import libeddsa_b200 as ed
+rng = np.random.default_rng(12)
+n = 200_000 + 37
+sec = rng.integers(0, 256, (n, 32), dtype=np.uint8); msgs = rng.integers(0, 256, (n, 64), dtype=np.uint8)
+pub = ed.ed25519_genpub_batch(sec); sig = ed.ed25519_sign_batch(sec, pub, msgs, fixed_len=64)
+bad = np.zeros(n, bool); bad[::9] = True; bad[[75_775, 75_776, 151_551, 151_552, n - 1]] = True
+sig[bad, 40] ^= 2
+dev = torch.device("cuda:0"); t = lambda a: torch.from_numpy(a).to(dev)
+ok = torch.empty(n, dtype=torch.uint8, device=dev)
+before = ed.launch_count()
+ed.ed25519_verify_batch_dev(ok, t(sig), t(pub), t(msgs), fixed_len=64); torch.cuda.synchronize()
+assert ed.launch_count() - before == 9, ed.launch_count() - before          # three passes of three kernels
+assert (ok.cpu().numpy().astype(bool) == ~bad).all()
+assert (ed.ed25519_verify_batch(sig, pub, msgs, fixed_len=64).astype(bool) == ~bad).all()
+lens = rng.integers(0, 150, n); off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+blob = rng.integers(0, 256, int(off[-1]) + 16, dtype=np.uint8)
+rsig = ed.ed25519_sign_batch(sec, pub, blob, off=off.astype(np.uint64)); rsig[bad, 3] ^= 1
+ed.ed25519_verify_batch_dev(ok, t(rsig), t(pub), t(blob), off=t(off)); torch.cuda.synchronize()
+assert (ok.cpu().numpy().astype(bool) == ~bad).all()
+print("ok")
+""" % (ROOT,)
+    res = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, EDDSA_B200_VERIFY_WAVES="1"), capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0 and "ok" in res.stdout, res.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------------------------ secrets
 def test_staging_buffers_are_scrubbed():
     """After a host-buffer call with secret inputs / outputs from ordinary (pageable) memory, the pinned host staging
