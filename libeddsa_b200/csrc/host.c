@@ -64,7 +64,7 @@ typedef struct {
     cudaStream_t kstream;                       /* verify: all kernels of the host-buffer pipeline run here, one after the other */
     cudaEvent_t in_ready[EDG_NSLOT], k_done[EDG_NSLOT];
     size_t verify_pass;                         /* signatures per full pass of the verify kernels (whole waves) */
-    size_t verify_wave, verify_chunk;           /* one wave of resident threads; chunk of the host-buffer pipeline (<= 4 waves) */
+    size_t verify_wave;                         /* one wave of resident threads of the loop kernel */
     uint8_t *h_in[EDG_NSLOT], *h_out[EDG_NSLOT];
     uint8_t *d_in[EDG_NSLOT], *d_out[EDG_NSLOT];
     size_t in_cap, out_cap;
@@ -208,7 +208,6 @@ static int dev_basic(int dev, edg_dev_t **out_ctx)
             CU(cudaStreamCreateWithFlags(&c->kstream, cudaStreamNonBlocking));
             c->verify_pass = edg_verify_pass(sms);
             c->verify_wave = c->verify_pass / edg_verify_waves();
-            c->verify_chunk = c->verify_wave * (edg_verify_waves() < 4 ? edg_verify_waves() : 4);   /* copies overlap kernels per chunk */
             /* scratch pool: freed blocks stay in the pool (no trimming at synchronisation points), so a steady
              * stream of calls allocates nothing after the first one */
             memset(&props, 0, sizeof props);
@@ -445,8 +444,8 @@ static void retire_slot(edg_dev_t *c, const edg_job_t *j, slot_t *sl, int s, int
 static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
 {
     int rc = 0, k, s, prev_dev = -1;
-    size_t pos, nshard = hi - lo, target, wave;
-    int staged = 0;
+    size_t pos, nshard = hi - lo, target, wave, budget;
+    int staged = 0, big_items;
     slot_t slot[EDG_NSLOT];
     int pin_in[3] = {0, 0, 0}, pin_msgs = 0, pin_out = 0;
     size_t chunk_no = 0;
@@ -462,32 +461,44 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
     /* aim for >= 4 chunks per shard (copy/compute overlap) but never tiny ones */
     target = (nshard + 3) / 4;
     if (target < 65536) target = 65536;
-    /* verify: chunks of whole passes of its kernels (whole waves of resident threads), kernels serialised on one
-     * stream so that the stages never share an SM (instruction cache) while copies overlap on the slot streams */
-    if (j->op == OP_VERIFY && nshard > c->verify_chunk) target = c->verify_chunk;
+    /* verify: chunks of whole waves of resident threads, kernels serialised on one stream so that the stages never
+     * share an SM (instruction cache) while copies overlap on the slot streams */
+    wave = j->op == OP_VERIFY && nshard > c->verify_wave && c->verify_wave >= 8 ? c->verify_wave : 0;
+    if (wave) target = c->verify_pass;
     if (target > nshard) target = nshard;
-    /* the first chunk's staging and copy are exposed, so chunks start small and grow: verify one wave first (then, when
-     * the inputs have to be staged through the pinned slots — a memcpy the GPU waits for — 1, 2 waves), the other
-     * operations 65536 items and four times more each chunk */
+    /* the first chunk's staging and copy are exposed, so chunks start small and grow — but every verify chunk is a pass
+     * of three kernels whose tails cost ~0.15 ms, so they grow fast: 1, 2, 12 waves, then whole passes (64-byte messages:
+     * a chunk's copy, 0.22 ms per wave, hides under the previous chunk's kernels, 1.44 ms per wave); 1, 1, 2, 4, 8 waves
+     * when the inputs have to be staged through the pinned slots (a memcpy the GPU waits for).  The other operations:
+     * 65536 items and four times more each chunk when staged. */
     for (k = 0; k < j->nin; k++) staged |= !pin_in[k];
     staged |= j->has_msgs && !pin_msgs;
-    wave = j->op == OP_VERIFY && target == c->verify_chunk && c->verify_wave >= 8 ? c->verify_wave : 0;
+    big_items = chunk_in_bytes(j, lo, hi) / nshard >= 768;      /* ~1 KB per item and up: the copies take as long as the kernels */
+    budget = 2 * g_chunk_bytes;
     for (pos = lo; pos < hi;) {
+        static const unsigned ramp_pinned[] = {1, 2, 12}, ramp_staged[] = {1, 1, 2, 4, 8};
         size_t m = target, in_bytes, out_bytes, ofs;
         uint8_t *d_in[3] = {NULL, NULL, NULL};
         const uint8_t *d_msgs = NULL;
         const unsigned long long *d_off = NULL;
         if (wave) {
-            if (chunk_no == 0) m = wave;
-            else if (staged && chunk_no == 1) m = wave;
-            else if (staged && chunk_no == 2) m = 2 * wave;
+            const size_t steps = staged ? sizeof ramp_staged / sizeof *ramp_staged : sizeof ramp_pinned / sizeof *ramp_pinned;
+            if (big_items) {
+                /* copies take as long as the kernels: a chunk larger than its predecessor stalls the GPU for the
+                 * difference, so the size stays constant — a sixteenth of the shard, in whole waves */
+                m = nshard / (16 * wave);
+                m = wave * (m < 1 ? 1 : m);
+            } else if (chunk_no < steps) m = wave * (staged ? ramp_staged : ramp_pinned)[chunk_no];
+            if (m > c->verify_pass) m = c->verify_pass;
         } else if (staged && chunk_no < 4) {
             m = (size_t)65536 << (2 * chunk_no);
             if (m > target) m = target;
         }
         if (pos + m > hi) m = hi - pos;
-        /* shrink the chunk until it fits the staging budget (ragged messages); a single oversized item grows the buffers */
-        while (m > 1 && chunk_in_bytes(j, pos, pos + m) > g_chunk_bytes) m = (m + 1) / 2;
+        /* shrink the chunk until it fits the staging budget (ragged messages); a single oversized item grows the buffers.
+         * Verify chunks stay whole waves as long as they can: 1.6 waves cost the loop kernel as much as 2. */
+        while (wave && m > wave && chunk_in_bytes(j, pos, pos + m) > budget) m = (m - 1) / wave * wave;
+        while (m > 1 && chunk_in_bytes(j, pos, pos + m) > budget) m = (m + 1) / 2;
         in_bytes = chunk_in_bytes(j, pos, pos + m);
         out_bytes = align_up(m * j->out_item);
         s = (int)(chunk_no % EDG_NSLOT);
