@@ -467,16 +467,18 @@ static int run_shard(edg_dev_t *c, const edg_job_t *j, size_t lo, size_t hi)
     if (wave) target = c->verify_pass;
     if (target > nshard) target = nshard;
     /* the first chunk's staging and copy are exposed, so chunks start small and grow — but every verify chunk is a pass
-     * of three kernels whose tails cost ~0.15 ms, so they grow fast: 1, 2, 12 waves, then whole passes (64-byte messages:
-     * a chunk's copy, 0.22 ms per wave, hides under the previous chunk's kernels, 1.44 ms per wave); 1, 1, 2, 4, 8 waves
-     * when the inputs have to be staged through the pinned slots (a memcpy the GPU waits for).  The other operations:
-     * 65536 items and four times more each chunk when staged. */
+     * of three kernels whose tails cost ~0.15 ms, so they double: 1, 2, 4, 8 waves, then whole passes (64-byte messages:
+     * a chunk's copy, 0.22 ms per wave alone and 0.5 ms when eight GPUs share the host's links, hides under the previous,
+     * half as large chunk's kernels, 1.44 ms per wave; jumping from 2 to 12 waves was 0.7 % faster on one GPU and stalled
+     * the ranks on the far side of an 8-GPU host for 1 ms); 1, 1, 2, 4, 8 waves when the inputs have to be staged through
+     * the pinned slots (a memcpy the GPU waits for).  The other operations: 65536 items and four times more each chunk
+     * when staged. */
     for (k = 0; k < j->nin; k++) staged |= !pin_in[k];
     staged |= j->has_msgs && !pin_msgs;
     big_items = chunk_in_bytes(j, lo, hi) / nshard >= 768;      /* ~1 KB per item and up: the copies take as long as the kernels */
     budget = 2 * g_chunk_bytes;
     for (pos = lo; pos < hi;) {
-        static const unsigned ramp_pinned[] = {1, 2, 12}, ramp_staged[] = {1, 1, 2, 4, 8};
+        static const unsigned ramp_pinned[] = {1, 2, 4, 8}, ramp_staged[] = {1, 1, 2, 4, 8};
         size_t m = target, in_bytes, out_bytes, ofs;
         uint8_t *d_in[3] = {NULL, NULL, NULL};
         const uint8_t *d_msgs = NULL;
