@@ -16,11 +16,11 @@
 
 namespace edg {
 
-// Every operation ends with one field inversion (254 S + 11 M: 27 % of a fixed-base operation, 8 % of
-// an X25519, 6 % of a verify).  The kernels therefore run each thread over up to EDG_BATCH operations
+// Every secret-key operation ends with one field inversion (254 S + 11 M: 46 % of the field work of a radix-64
+// fixed-base operation, 10 % of an X25519; verify compares projectively and needs none).  The kernels therefore run each thread over up to EDG_BATCH operations
 // in three phases — *_front (everything up to the projective result), ONE shared inversion for the
 // thread's whole batch (Montgomery's trick: 3 multiplications per element), *_back (encode / hash /
-// compare) — which removes 7/8 of the inversions.  The single-operation functions below (used by the
+// compare) — which removes up to 31/32 of the inversions.  The single-operation functions below (used by the
 // host-side unit tests) are front + fe_inv + back, so both paths execute the same code.
 #ifndef EDG_BATCH
 #define EDG_BATCH 32     /* measured at 2^20: 8 -> 16 -> 32 gives +1.5 % and +1.7 % on genpub / x25519_base, +1.4 % and +0.7 % on sign */

@@ -1,7 +1,7 @@
 // Scalars modulo the group order L = 2^252 + 27742317777372353535851937790883648493, one per thread.
 //
 // Role of the reference's lib/sc.c: sc_barrett (sc.c:79-158), sc_import (sc.c:191), sc_export /
-// sc_reduce (sc.c:221,164), sc_mul + sc_add (sc.c:241, sc.h:53) and the signed radix-16 recoding
+// sc_reduce (sc.c:221,164), sc_mul + sc_add (sc.c:241, sc.h:53) and the signed radix-2^W recoding
 // that ed_scale_base derives from con_off (sc.c:40, ed.c:406-422).  Re-designed for 32-bit
 // registers: eight saturated 32-bit words, Barrett (HAC 14.42) with b = 2^32, k = 8,
 // mu = floor(2^512 / L); every loop has constant trip count, every select is a mask — no branch
