@@ -130,20 +130,10 @@ __global__ void __launch_bounds__(EDG_COMB_LB_THREADS, EDG_COMB_BLOCKS) k_comb(s
     }
 }
 
-// comb table in fragment order for ge_pre_select_mma: word [row][(nt * H + h) * 32 + lane] = bytes of entries
-// 16h + 4q .. 16h + 4q + 3 (q = lane % 4) at entry byte 4 (6 (g / 2) + nt / 2) + 2 (nt % 2) + g % 2, g = lane / 4
+// comb table in fragment order for ge_pre_select_mma (ops.cuh: comb_mma_word)
 __global__ void k_comb_layout(u32 *mma, const u32 *table) {
-    constexpr unsigned H = EDG_COMB_ENTRIES / 16 ? EDG_COMB_ENTRIES / 16 : 1;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= EDG_COMB_WORDS) return;
-    const unsigned row = idx / (EDG_COMB_ENTRIES * 24), rem = idx % (EDG_COMB_ENTRIES * 24), nt = rem / (32 * H), h = rem / 32 % H, lane = rem % 32;
-    const unsigned g = lane >> 2, q = lane & 3, byte = 4 * (6 * (g / 2) + nt / 2) + 2 * (nt % 2) + g % 2;
-    u32 w = 0;
-    for (unsigned i = 0; i < 4; i++) {
-        const u32 *entry = table + ((size_t)row * EDG_COMB_ENTRIES + 16 * h + 4 * q + i) * 24;
-        w |= ((entry[byte >> 2] >> (8 * (byte & 3))) & 0xffu) << (8 * i);
-    }
-    mma[idx] = w;
+    if (idx < EDG_COMB_WORDS) mma[idx] = comb_mma_word(table, idx);
 }
 
 // a[i] = clamp(SHA512(sec[i])[0..31]) mod L                                     [ed25519_key_setup, ed25519-sha512.c:31-47, :62]

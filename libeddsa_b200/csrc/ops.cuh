@@ -370,6 +370,21 @@ EDG_HD void comb_table_row(u32 *row, const u32 *base) {
     for (u32 g = 0; g < EDG_COMB_ENTRIES / 8; g++) wtab_build8(row + 24u * 8u * g, base, 8u * g + 1u);
 }
 
+// Word idx of the comb table in FRAGMENT ORDER (what ge_pre_select_mma reads; built by k_comb_layout): row-major over
+// [row][(nt * H + h) * 32 + lane], H = EDG_COMB_ENTRIES / 16: the bytes of entries 16h + 4q .. 16h + 4q + 3 (q = lane % 4) at
+// entry byte 4 (6 (g / 2) + nt / 2) + 2 (nt % 2) + g % 2, g = lane / 4 — column g of byte-tile nt of the B operand.
+EDG_HD u32 comb_mma_word(const u32 *table, unsigned idx) {
+    const unsigned H = EDG_COMB_ENTRIES / 16 ? EDG_COMB_ENTRIES / 16 : 1;
+    const unsigned row = idx / (EDG_COMB_ENTRIES * 24), rem = idx % (EDG_COMB_ENTRIES * 24), nt = rem / (32 * H), h = rem / 32 % H, lane = rem % 32;
+    const unsigned g = lane >> 2, q = lane & 3, byte = 4 * (6 * (g / 2) + nt / 2) + 2 * (nt % 2) + g % 2;
+    u32 w = 0;
+    for (unsigned i = 0; i < 4; i++) {
+        const u32 *entry = table + ((size_t)row * EDG_COMB_ENTRIES + 16 * h + 4 * q + i) * 24;
+        w |= ((entry[byte >> 2] >> (8 * (byte & 3))) & 0xffu) << (8 * i);
+    }
+    return w;
+}
+
 // entry |digit| of a window table in global memory, negated when digit < 0 (public data: direct index)
 EDG_HD void ge_pre_load_wtab(ge_pre &t, const u32 *tbl, int digit) {
     const u32 neg = (u32)(digit >> 31);

@@ -24,6 +24,54 @@ static const u32 *host_comb() {
 #define BASE_COMB host_comb()
 extern "C" {
 const uint32_t *hs_comb(int *rows, int *entries) { *rows = EDG_COMB_ROWS; *entries = EDG_COMB_ENTRIES; return host_comb(); }
+// Emulation of the tensor-core table lookup (ge.cuh: ge_pre_select_mma) for one warp, with the fragment layouts of
+// mma.sync.m16n8k16 / m16n8k32 .u8 as the PTX ISA defines them (A: thread (g, q) holds rows g, g + 8 at k = 4q + i (+16);
+// B: k = 4q + i (+16), column g; D: rows g, g + 8, columns 2q, 2q + 1).  It reads the fragment-order table built by the
+// SAME comb_mma_word() the device uses and reproduces the device's one-hot construction, byte packing and exchange-area
+// indexing: out[lane][24] must be entry |digit_lane| of the row (all zero for digit 0).
+void hs_mma_select(uint32_t *out, int row, const uint32_t *absd) {
+    const u32 *std_tab = host_comb();
+    const int H = EDG_COMB_ENTRIES / 16;
+    static u32 *mma = 0;
+    if (!mma) { mma = new u32[EDG_COMB_WORDS]; for (unsigned i = 0; i < EDG_COMB_WORDS; i++) mma[i] = comb_mma_word(std_tab, i); }
+    const u32 *row_mma = mma + (size_t)row * EDG_COMB_ENTRIES * 24;
+    u32 xchg[32 * 28], A[32][4][2];
+    for (unsigned lane = 0; lane < 32; lane++) {           // every thread's A fragments, by the device's formula
+        const unsigned g = lane >> 2, q = lane & 3;
+        for (int r = 0; r < 4; r++)
+            for (int h = 0; h < H; h++) {
+                const u32 x = absd[g + 8 * r] - 1u - 16u * h - 4u * q;
+                const u32 hit = 0u - ((((x >> 2) - 1u) >> 31));
+                A[lane][r][h] = (1u << ((x & 3u) * 8u)) & hit;
+            }
+    }
+    for (unsigned lane = 0; lane < 32; lane++) {
+        const unsigned g = lane >> 2, q = lane & 3;
+        for (int m = 0; m < 6; m++)
+            for (int mt = 0; mt < 2; mt++) {
+                u32 d[2][4];                                   // the two byte-tiles 2m, 2m + 1
+                for (int s = 0; s < 2; s++)
+                    for (int c = 0; c < 4; c++) {              // c0, c1: row g; c2, c3: row g + 8; columns 2q + (c & 1)
+                        const int rr = 2 * mt + (c >> 1), col = 2 * q + (c & 1);
+                        // D[row][col] = sum_k A[row][k] B[k][col] over k = 0 .. 16H - 1.  A[row g + 8 rr][k] is byte k % 4 of word
+                        // k / 16 of thread (g, (k % 16) / 4); B[k][col] is byte k % 4 of word k / 16 of thread (col, (k % 16) / 4)
+                        u32 sum = 0;
+                        for (int k = 0; k < 16 * H; k++) {
+                            const u32 aw = A[4 * g + (k % 16) / 4][rr][k / 16];
+                            const u32 bw = row_mma[((2 * m + s) * H + k / 16) * 32 + 4 * col + (k % 16) / 4];
+                            sum += ((aw >> (8 * (k % 4))) & 0xffu) * ((bw >> (8 * (k % 4))) & 0xffu);
+                        }
+                        d[s][c] = sum;
+                    }
+                const u32 lo = (d[0][0] & 0xff) | (d[0][1] & 0xff) << 8 | (d[1][0] & 0xff) << 16 | (d[1][1] & 0xff) << 24;
+                const u32 hi = (d[0][2] & 0xff) | (d[0][3] & 0xff) << 8 | (d[1][2] & 0xff) << 16 | (d[1][3] & 0xff) << 24;
+                xchg[(g + 16 * mt) * 28 + 6 * q + m] = lo;
+                xchg[(g + 8 + 16 * mt) * 28 + 6 * q + m] = hi;
+            }
+    }
+    for (int lane = 0; lane < 32; lane++)
+        for (int i = 0; i < 24; i++) out[24 * lane + i] = xchg[lane * 28 + i];
+}
 void hs_x25519(uint8_t *out, const uint8_t *scalar, const uint8_t *point) {
     u32 o[8], s[8], p[8]; memcpy(s, scalar, 32); memcpy(p, point, 32); x25519_op(o, s, p); memcpy(out, o, 32);
 }

@@ -231,6 +231,31 @@ def test_comb_table_host_build(ops):
     em.check_comb_table(raw, w)
 
 
+def test_tensor_core_lookup_layout(ops):
+    """The fragment-order comb table (comb_mma_word, the code k_comb_layout runs) together with the lookup's indexing —
+    which thread's product lands in which word of which lane's exchange area — emulated with the PTX fragment layouts
+    of mma.sync.m16n8k32.u8: every lane must receive exactly entry |digit| of the row, for every |digit| 0 .. ENTRIES."""
+    rows, entries = ctypes.c_int(), ctypes.c_int()
+    ops.hs_comb.restype = ctypes.POINTER(ctypes.c_uint32)
+    tab = ops.hs_comb(ctypes.byref(rows), ctypes.byref(entries))
+    rows, entries = rows.value, entries.value
+    if entries < 16:
+        pytest.skip("the tensor-core lookup needs rows of 16 or 32 entries")
+    std = np.ctypeslib.as_array(tab, shape=(rows, entries, 24))
+    rng = random.Random(9)
+    out = (ctypes.c_uint32 * (32 * 24))()
+    for row in (0, 1, rows // 2, rows - 1):
+        for trial in range(3):
+            absd = [rng.randrange(entries + 1) for _ in range(32)]
+            if trial == 0:
+                absd = [(l * 5 + row) % (entries + 1) for l in range(32)]      # every value 0 .. ENTRIES occurs
+            ops.hs_mma_select(out, row, (ctypes.c_uint32 * 32)(*absd))
+            got = np.ctypeslib.as_array(out).reshape(32, 24)
+            for lane, d in enumerate(absd):
+                want = std[row, d - 1] if d else np.zeros(24, np.uint32)
+                assert (got[lane] == want).all(), (row, lane, d)
+
+
 def test_half_gcd(ops):
     """hgcd.cuh: (rho, tau) is a lattice vector (tau = rho t mod 8L), rho is odd, and both are short — for random t,
     for structured t (tiny, huge partial quotients, even-rho traps) and for the documented fallback."""
