@@ -575,15 +575,22 @@ out:
         s = (int)((chunk_no + k) % EDG_NSLOT); /* oldest first */
         if (slot[s].inflight) {
             cudaError_t e = rc ? cudaSuccess : cudaEventSynchronize(c->done[s]);
-            if (e != cudaSuccess && !rc) rc = fail((int)e, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess && !rc) {
+                rc = fail((int)e, "cudaEventSynchronize failed: %s", cudaGetErrorString(e));
+                cudaDeviceSynchronize();        /* the younger chunks are not waited for one by one any more: nothing may still
+                                                 * be running (or writing to the caller's memory) when the call returns */
+            }
             retire_slot(c, j, &slot[s], s, pin_out, !rc);
         }
     }
     if (rc && !g_no_scrub && (op_secret_in(j->op) || op_secret_out(j->op))) {
-        /* error path: wipe the device copies the queued memsets may not have reached */
+        /* error path: wipe the device copies the queued memsets may not have reached, and the host slots whole — the
+         * chunk that failed had staged its keys but was not in flight yet, so retire_slot never saw it */
         for (k = 0; k < EDG_NSLOT; k++) {
             if (c->d_in[k]) cudaMemset(c->d_in[k], 0, c->in_cap);
             if (c->d_out[k]) cudaMemset(c->d_out[k], 0, c->out_cap);
+            if (c->h_in[k]) memset(c->h_in[k], 0, c->in_cap);
+            if (c->h_out[k] && op_secret_out(j->op)) memset(c->h_out[k], 0, c->out_cap);
         }
     }
     if (prev_dev >= 0 && prev_dev != c->dev) cudaSetDevice(prev_dev);

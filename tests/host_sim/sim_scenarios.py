@@ -1,0 +1,688 @@
+"""TEST INFRASTRUCTURE: scenarios for the host layer (libeddsa_b200/csrc/host.c) on the CUDA runtime simulator
+(tests/host_sim/cudasim.cpp).  tests/test_host_pipeline.py runs each scenario in a fresh interpreter
+
+    python tests/host_sim/sim_scenarios.py <scenario>
+
+because host.c reads its environment once per process.  The product binding (libeddsa_b200/__init__.py) is used as it
+is; only its library path is pointed at tests/host_sim/libeddsa_sim.so = host.c + the simulator.  Results are checked
+against the CPU reference / oracle (tests/cpu_ref.py).
+"""
+import ctypes
+import os
+import sys
+import threading
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+TESTS = os.path.dirname(HERE)
+ROOT = os.path.dirname(TESTS)
+for p in (ROOT, TESTS):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+SIM_SO = os.environ.get("CUDASIM_SO") or os.path.join(HERE, "libeddsa_sim.so")      # override: the mutants of test_host_pipeline.py
+EINVAL = -1
+(API_MALLOC, API_MALLOC_HOST, API_MEMCPY_ASYNC, API_MEMSET_ASYNC, API_EVENT_RECORD, API_EVENT_SYNC, API_STREAM_WAIT, API_POOL_ALLOC,
+ API_FREE_ASYNC, API_STREAM_CREATE, API_EVENT_CREATE, API_LAUNCH, API_SET_DEVICE, API_POOL_CREATE, API_KERNEL_FAULT, API_STREAM_SYNC) = range(16)
+API_NAMES = ["cudaMalloc", "cudaMallocHost", "cudaMemcpyAsync", "cudaMemsetAsync", "cudaEventRecord", "cudaEventSynchronize", "cudaStreamWaitEvent",
+             "cudaMallocFromPoolAsync", "cudaFreeAsync", "cudaStreamCreate", "cudaEventCreate", "kernel launch", "cudaSetDevice", "cudaMemPoolCreate",
+             "kernel fault", "cudaStreamSynchronize"]
+L_X25519, L_X25519_BASE, L_GENPUB, L_SIGN, L_VERIFY, L_PK_CONV, L_SK_CONV, L_FE_TEST, L_SC_TEST, L_TABLES = range(10)
+K_DEVICE, K_PINNED = 0, 1
+STAT_NAMES = ["h2d_bytes", "d2h_bytes", "h2d_copies", "d2h_copies", "kernels", "pageable_async", "memsets", "dev_allocs", "host_allocs", "pool_allocs",
+              "max_chunk_items", "event_syncs"]
+P = 2**255 - 19
+
+
+class Sim:
+    """The simulator's control surface + the product binding loaded on top of it."""
+
+    def __init__(self):
+        import libeddsa_b200 as ed
+        ed.LIB_PATH = SIM_SO
+        self.ed = ed
+        self.L = L = ed.lib()
+        vp, sz = ctypes.c_void_p, ctypes.c_size_t
+        L.cudasim_error_count.restype = ctypes.c_uint64
+        L.cudasim_first_error.restype = ctypes.c_char_p
+        L.cudasim_fail.argtypes = [ctypes.c_int, ctypes.c_long]
+        L.cudasim_stats.argtypes = [vp]
+        L.cudasim_launch_log.argtypes = [vp, sz]
+        L.cudasim_launch_log.restype = sz
+        L.cudasim_pending_ops.restype = sz
+        L.cudasim_live_allocs.argtypes = [ctypes.c_int, vp]
+        L.cudasim_live_allocs.restype = sz
+        L.cudasim_find.argtypes = [vp, sz, sz]
+        L.cudasim_find.restype = sz
+        L.cudasim_user_alloc.argtypes = [sz, ctypes.c_int, ctypes.c_int]
+        L.cudasim_user_alloc.restype = vp
+        L.cudasim_user_free.argtypes = [vp]
+        L.cudasim_stream_create.argtypes = [ctypes.c_int]
+        L.cudasim_stream_create.restype = vp
+        L.cudasim_set_device.argtypes = [ctypes.c_int]
+        L.cudasim_config.argtypes = [ctypes.c_int] * 3
+
+    def errors(self):
+        return int(self.L.cudasim_error_count())
+
+    def first_error(self):
+        return self.L.cudasim_first_error().decode()
+
+    def stats(self):
+        buf = (ctypes.c_uint64 * 12)()
+        self.L.cudasim_stats(buf)
+        return dict(zip(STAT_NAMES, [int(x) for x in buf]))
+
+    def reset(self):
+        self.L.cudasim_reset_stats()
+
+    def launches(self, op=None):
+        buf = (ctypes.c_uint64 * (3 * 4096))()
+        k = self.L.cudasim_launch_log(buf, 4096)
+        rows = [(int(buf[3 * i]), int(buf[3 * i + 1]), int(buf[3 * i + 2])) for i in range(min(k, 4096))]
+        return [r for r in rows if r[1] != L_TABLES and (op is None or r[1] == op)]
+
+    def pending(self):
+        return int(self.L.cudasim_pending_ops())
+
+    def live(self, kind=-1):
+        b = ctypes.c_uint64(0)
+        k = self.L.cudasim_live_allocs(kind, ctypes.byref(b))
+        return int(k), int(b.value)
+
+    def find(self, rows, width=16):
+        """How often the first `width` bytes of any of the rows occur in memory the library owns."""
+        blob = b"".join(bytes(r[:width]) for r in rows)
+        return int(self.L.cudasim_find(blob, len(blob) // width, width))
+
+    def user_array(self, nbytes, kind, dev=0):
+        """A caller-owned buffer the simulator knows as page-locked host memory (kind 1) or device memory (kind 0)."""
+        p = self.L.cudasim_user_alloc(max(nbytes, 1), kind, dev)
+        arr = np.ctypeslib.as_array((ctypes.c_uint8 * max(nbytes, 1)).from_address(p))[:nbytes]
+        return arr, p
+
+    def clean(self, pageable_ok=False):
+        """After a successful call: no simulator complaints, nothing left queued, no async copy touched pageable memory."""
+        assert self.errors() == 0, self.first_error()
+        assert self.pending() == 0, f"{self.pending()} operations still queued after the call returned"
+        if not pageable_ok:
+            assert self.stats()["pageable_async"] == 0, "cudaMemcpyAsync on pageable memory (serialises on real hardware)"
+
+
+def rng(seed):
+    return np.random.default_rng(seed)
+
+
+def rand_rows(r, n, width=32):
+    return r.integers(0, 256, size=(n, width), dtype=np.uint8)
+
+
+def make_signed(cpu, r, n, fixed_len=None, max_len=0):
+    """n key pairs, messages (fixed length or ragged 0..max_len) and their signatures from the CPU checker."""
+    sec = rand_rows(r, n)
+    pub = cpu.genpub(sec)
+    if fixed_len is not None:
+        msgs = r.integers(0, 256, size=n * fixed_len, dtype=np.uint8)
+        off = None
+        sig = cpu.sign(sec, pub, msgs, None, fixed_len)
+    else:
+        lens = r.integers(0, max_len + 1, size=n)
+        off = np.zeros(n + 1, np.uint64)
+        off[1:] = np.cumsum(lens)
+        msgs = r.integers(0, 256, size=int(off[-1]) + 1, dtype=np.uint8)
+        sig = cpu.sign(sec, pub, msgs, off, 0)
+    return sec, pub, msgs, off, sig
+
+
+def mutate(r, sig, pub, frac=0.1):
+    """Corrupt a fraction of the rows (signature or key bits); returns the copies."""
+    sig, pub = sig.copy(), pub.copy()
+    n = len(sig)
+    for i in r.choice(n, size=max(1, int(n * frac)), replace=False) if n else []:
+        if r.integers(0, 2):
+            sig[i, r.integers(0, 64)] ^= 1 << r.integers(0, 8)
+        else:
+            pub[i, r.integers(0, 32)] ^= 1 << r.integers(0, 8)
+    return sig, pub
+
+
+def eq(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape and (a == b).all(), f"{what}: {int((a != b).sum())} bytes differ"
+
+
+def fe_add_expected(a, b):
+    """(a + b) mod p for n x 32-byte little-endian rows, as canonical bytes, compared modulo p by the caller."""
+    return [(int.from_bytes(bytes(x), "little") + int.from_bytes(bytes(y), "little")) % P for x, y in zip(a, b)]
+
+
+def check_fe_add(out, a, b, sample=None):
+    idx = range(len(a)) if sample is None else sample
+    for i in idx:
+        got = int.from_bytes(bytes(out[i]), "little") % P
+        want = (int.from_bytes(bytes(a[i]), "little") + int.from_bytes(bytes(b[i]), "little")) % P
+        assert got == want, f"fe add row {i}"
+
+
+# ======================================================================================================================
+def scenario_all_ops():
+    """Every batch entry point, small and awkward sizes, against the CPU checker; the simulator sees a clean run."""
+    from cpu_ref import best_cpu_impl, Oracle
+    sim, cpu, orc = Sim(), best_cpu_impl(), Oracle()
+    ed = sim.ed
+    r = rng(1)
+    for n in (0, 1, 2, 31, 32, 33, 257):
+        sec, pub, msgs, off, sig = make_signed(cpu, r, n, fixed_len=37)
+        eq(ed.ed25519_genpub_batch(sec), pub, f"genpub n={n}")
+        sim.clean()
+        eq(ed.ed25519_sign_batch(sec, pub, msgs, None, 37), sig, f"sign n={n}")
+        sim.clean()
+        bad_sig, bad_pub = mutate(r, sig, pub, 0.3) if n else (sig, pub)
+        eq(ed.ed25519_verify_batch(bad_sig, bad_pub, msgs, None, 37), cpu.verify(bad_sig, bad_pub, msgs, None, 37), f"verify n={n}")
+        sim.clean()
+        if n:
+            assert ed.ed25519_verify_batch(sig, pub, msgs, None, 37).all()
+        pts = rand_rows(r, n)
+        eq(ed.x25519_batch(sec, pts), cpu.x25519(sec, pts), f"x25519 n={n}")
+        eq(ed.x25519_base_batch(sec), cpu.x25519_base(sec), f"x25519_base n={n}")
+        sim.clean()
+        pk, sk = ed.pk_ed25519_to_x25519_batch(pub), ed.sk_ed25519_to_x25519_batch(sec)
+        for i in range(0, n, 17):
+            assert bytes(pk[i]) == orc.pk_to_x25519(bytes(pub[i])) and bytes(sk[i]) == orc.sk_to_x25519(bytes(sec[i]))
+        sim.clean()
+    # zero-length messages and a NULL blob are legal when nothing is hashed
+    sec, pub, msgs, off, sig = make_signed(cpu, r, 5, fixed_len=0)
+    eq(ed.ed25519_sign_batch(sec, pub, None, None, 0), sig, "sign of empty messages")
+    assert ed.ed25519_verify_batch(sig, pub, None, None, 0).all()
+    # argument errors: EINVAL, a message, nothing launched
+    L = sim.L
+    before = ed.launch_count()
+    assert L.ed25519_genpub_batch(3, None, sec.ctypes.data) == EINVAL and b"NULL" in L.eddsa_b200_last_error()
+    assert L.ed25519_verify_batch(3, sig.ctypes.data, sig.ctypes.data, pub.ctypes.data, None, None, 5) == EINVAL
+    dec = np.array([0, 5, 3, 9], np.uint64)
+    assert L.ed25519_verify_batch(3, sig.ctypes.data, sig.ctypes.data, pub.ctypes.data, sig.ctypes.data, dec.ctypes.data, 0) == EINVAL
+    assert b"non-decreasing" in L.eddsa_b200_last_error()
+    assert ed.launch_count() == before
+    sim.clean()
+
+
+def scenario_chunks():
+    """The chunk schedule of run_shard (one simulated SM: a verify wave is 512 signatures, a pass 8192)."""
+    from cpu_ref import best_cpu_impl
+    assert os.environ.get("CUDASIM_SMS") == "1" and os.environ.get("CUDASIM_DEVICES") == "1"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(2)
+    n = 20037
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, fixed_len=64)
+    bad_sig, bad_pub = mutate(r, sig, pub, 0.1)
+    want = cpu.verify(bad_sig, bad_pub, msgs, None, 64)
+    assert 0 < want.sum() < n
+    # ordinary memory: chunks of 1, 1, 2, 4, 8 waves, then whole passes
+    sim.reset()
+    eq(ed.ed25519_verify_batch(bad_sig, bad_pub, msgs, None, 64), want, "verify from pageable memory")
+    sim.clean()
+    assert [x[2] for x in sim.launches(L_VERIFY)] == [512, 512, 1024, 2048, 4096, 8192, 3653], sim.launches(L_VERIFY)
+    st = sim.stats()
+    assert st["h2d_bytes"] == n * (64 + 32 + 64) and st["d2h_bytes"] == n and st["d2h_copies"] == 7
+    # page-locked caller memory: used directly, chunks of 1, 2, 4, 8 waves, then whole passes
+    bufs = {}
+    for name, arr in (("sig", bad_sig), ("pub", bad_pub), ("msgs", msgs), ("ok", np.zeros(n, np.uint8))):
+        a, p = sim.user_array(arr.nbytes, K_PINNED)
+        a[:] = arr.reshape(-1)
+        bufs[name] = (a, p)
+    sim.reset()
+    rc = L.ed25519_verify_batch(n, bufs["ok"][1], bufs["sig"][1], bufs["pub"][1], bufs["msgs"][1], None, 64)
+    assert rc == 0, L.eddsa_b200_last_error()
+    eq(bufs["ok"][0], want, "verify from page-locked memory")
+    sim.clean()
+    assert [x[2] for x in sim.launches(L_VERIFY)] == [512, 1024, 2048, 4096, 8192, 4165], sim.launches(L_VERIFY)
+    # mixed: only the output is page-locked
+    sim.reset()
+    bufs["ok"][0][:] = 7
+    rc = L.ed25519_verify_batch(n, bufs["ok"][1], bad_sig.ctypes.data, bad_pub.ctypes.data, msgs.ctypes.data, None, 64)
+    assert rc == 0
+    eq(bufs["ok"][0], want, "verify into a page-locked result array")
+    sim.clean()
+    # ~1 KB items: copies take as long as the kernels, the chunk size stays constant (a sixteenth of the shard in whole waves)
+    n2 = 10000
+    sec2, pub2, msgs2, off2, sig2 = make_signed(cpu, r, n2, fixed_len=1024)
+    sig2[::7, 3] ^= 4
+    sim.reset()
+    eq(ed.ed25519_verify_batch(sig2, pub2, msgs2, None, 1024), cpu.verify(sig2, pub2, msgs2, None, 1024), "verify of 1 KB messages")
+    sim.clean()
+    sizes = [x[2] for x in sim.launches(L_VERIFY)]
+    assert sizes == [512] * 19 + [n2 - 19 * 512], sizes
+    # the other operations: 65536 items and four times more each chunk when staged; quarters of the shard when page-locked
+    n3 = 300000
+    a, b = rand_rows(r, n3), rand_rows(r, n3)
+    sim.reset()
+    out = ed.fe_selftest(a, b, 2)
+    check_fe_add(out, a, b, range(0, n3, 997))
+    check_fe_add(out, a, b, [65535, 65536, 140535, 140536, n3 - 1])
+    sim.clean()
+    assert [x[2] for x in sim.launches(L_FE_TEST)] == [65536, 75000, 75000, 75000, 9464], sim.launches(L_FE_TEST)
+    pa, pb, po = sim.user_array(a.nbytes, K_PINNED), sim.user_array(b.nbytes, K_PINNED), sim.user_array(a.nbytes, K_PINNED)
+    pa[0][:] = a.reshape(-1)
+    pb[0][:] = b.reshape(-1)
+    sim.reset()
+    assert L.eddsa_b200_fe_selftest(n3, po[1], pa[1], pb[1], 2) == 0
+    check_fe_add(po[0].reshape(-1, 32), a, b, range(0, n3, 997))
+    sim.clean()
+    assert [x[2] for x in sim.launches(L_FE_TEST)] == [75000] * 4
+
+
+def scenario_budget():
+    """EDDSA_B200_CHUNK_MB=1: chunks shrink to the staging budget; one item larger than the budget grows the buffers."""
+    from cpu_ref import best_cpu_impl
+    assert os.environ.get("EDDSA_B200_CHUNK_MB") == "1"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed = sim.ed
+    r = rng(3)
+    n = 100000
+    a, b = rand_rows(r, n), rand_rows(r, n)
+    sim.reset()
+    out = ed.fe_selftest(a, b, 2)
+    check_fe_add(out, a, b, range(0, n, 499))
+    sim.clean()
+    sizes = [x[2] for x in sim.launches(L_FE_TEST)]
+    assert max(sizes) == 32768 and sum(sizes) == n, sizes      # 2 x 32 bytes per item, 2 MB budget
+    # ragged messages, lengths 0..300, one of 3 MB in the middle (over budget: the pipeline drains and re-allocates)
+    n = 3000
+    sec = rand_rows(r, n)
+    pub = cpu.genpub(sec)
+    lens = r.integers(0, 301, size=n)
+    lens[1234] = 3 << 20
+    lens[5] = 0
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    msgs = r.integers(0, 256, size=int(off[-1]), dtype=np.uint8)
+    want_sig = cpu.sign(sec, pub, msgs, off, 0)
+    sim.reset()
+    sig = ed.ed25519_sign_batch(sec, pub, msgs, off, 0)
+    eq(sig, want_sig, "ragged sign with a 3 MB message")
+    sim.clean()
+    assert len(sim.launches(L_SIGN)) >= 3
+    bad_sig, bad_pub = mutate(r, sig, pub, 0.2)
+    bad_sig[1234, 40] ^= 1
+    sim.reset()
+    eq(ed.ed25519_verify_batch(bad_sig, bad_pub, msgs, off, 0), cpu.verify(bad_sig, bad_pub, msgs, off, 0), "ragged verify with a 3 MB message")
+    sim.clean()
+    lg = sim.launches(L_VERIFY)
+    assert sum(x[2] for x in lg) == n and any(x[2] == 1 for x in lg), lg       # the big message travels alone
+
+
+def scenario_multi():
+    """Sharding over four simulated devices: contiguous index ranges, fewer devices for small batches, the caller's device kept."""
+    from cpu_ref import best_cpu_impl
+    assert os.environ.get("CUDASIM_DEVICES") == "4"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(4)
+    assert ed.device_count() == 4
+    L.cudasim_set_device(3)                                     # the caller works on device 3
+    n = 100001
+    a, b = rand_rows(r, n), rand_rows(r, n)
+    sim.reset()
+    out = ed.fe_selftest(a, b, 2)
+    check_fe_add(out, a, b, list(range(0, n, 499)) + [24999, 25000, 25001, 50000, 75000, 75001, n - 1])
+    sim.clean()
+    lg = sorted(sim.launches(L_FE_TEST))
+    assert [(d, m) for d, _, m in lg] == [(0, 25000), (1, 25000), (2, 25000), (3, 25001)], lg
+    assert L.cudasim_current_device() == 3
+    for n_small, want_devs in ((16384, 1), (16385, 2), (40000, 3), (65536, 4)):
+        sim.reset()
+        out = ed.fe_selftest(a[:n_small], b[:n_small], 3)
+        sim.clean()
+        assert len({d for d, _, _ in sim.launches(L_FE_TEST)}) == want_devs, (n_small, sim.launches(L_FE_TEST))
+    ed.set_device_count(2)
+    assert ed.device_count() == 2
+    sim.reset()
+    sec = rand_rows(r, 40000)
+    eq(ed.ed25519_genpub_batch(sec), cpu.genpub(sec), "genpub over two devices")
+    sim.clean()
+    assert sorted((d, m) for d, _, m in sim.launches(L_GENPUB)) == [(0, 20000), (1, 20000)]
+    ed.set_device_count(0)
+    assert ed.device_count() == 4
+    assert L.eddsa_b200_set_device_count(5) == EINVAL
+    # verify with mutated rows over all four devices, ragged messages, result identical to the checker
+    n = 50000
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, max_len=40)
+    bad_sig, bad_pub = mutate(r, sig, pub, 0.1)
+    sim.reset()
+    eq(ed.ed25519_verify_batch(bad_sig, bad_pub, msgs, off, 0), cpu.verify(bad_sig, bad_pub, msgs, off, 0), "verify over four devices")
+    sim.clean()
+    assert {d for d, _, _ in sim.launches(L_VERIFY)} == {0, 1, 2, 3}
+    assert L.cudasim_current_device() == 3
+    # a single operation runs on the first configured device and leaves the caller's device alone
+    sim.reset()
+    assert ed.ed25519_verify(bytes(sig[0]), bytes(pub[0]), bytes(msgs[int(off[0]):int(off[1])]))
+    assert [d for d, _, _ in sim.launches()] == [0] and L.cudasim_current_device() == 3
+
+
+def scenario_device_list():
+    """EDDSA_B200_DEVICES="2,0": the shards go to device 2 and device 0, in that order."""
+    assert os.environ.get("EDDSA_B200_DEVICES") == "2,0"
+    sim = Sim()
+    ed = sim.ed
+    r = rng(5)
+    assert ed.device_count() == 2
+    n = 50000
+    a, b = rand_rows(r, n), rand_rows(r, n)
+    a[:25000, 0] = 1
+    a[25000:, 0] = 2
+    sim.reset()
+    out = ed.fe_selftest(a, b, 2)
+    check_fe_add(out, a, b, range(0, n, 211))
+    sim.clean()
+    assert sorted((d, m) for d, _, m in sim.launches(L_FE_TEST)) == [(0, 25000), (2, 25000)]
+    assert sim.live()[0] > 0
+    # only devices 2 and 0 have contexts
+    ed.shutdown()
+    assert sim.live() == (0, 0)
+
+
+def scenario_scrub():
+    """No copy of a secret input or output survives a call in any buffer the library owns (staging slots on both sides,
+    kernel scratch) — with EDDSA_B200_DEBUG_NO_SCRUB=1 (negative control) the same search finds them."""
+    from cpu_ref import best_cpu_impl
+    negative = os.environ.get("EDDSA_B200_DEBUG_NO_SCRUB") == "1"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(6)
+    n = 3000
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, fixed_len=20)
+    pts = rand_rows(r, n)
+    sample = list(range(0, n, 97)) + [n - 1]
+
+    def residue(rows):
+        return sim.find([rows[i] for i in sample])
+
+    found = {}
+    ed.ed25519_genpub_batch(sec)
+    found["genpub"] = residue(sec)
+    ed.ed25519_sign_batch(sec, pub, msgs, None, 20)
+    found["sign"] = residue(sec)
+    out = ed.x25519_batch(sec, pts)
+    found["x25519"] = residue(sec)
+    found["x25519 out"] = residue(out)
+    ed.x25519_base_batch(sec)
+    found["x25519_base"] = residue(sec)
+    out = ed.sk_ed25519_to_x25519_batch(sec)
+    found["sk_convert"] = residue(sec)
+    found["sk_convert out"] = residue(out)
+    # page-locked caller memory: nothing is staged on the host, the device slots are still wiped
+    ps, pp, po = sim.user_array(sec.nbytes, K_PINNED), sim.user_array(pts.nbytes, K_PINNED), sim.user_array(sec.nbytes, K_PINNED)
+    ps[0][:] = sec.reshape(-1)
+    pp[0][:] = pts.reshape(-1)
+    assert L.x25519_batch(n, po[1], ps[1], pp[1]) == 0
+    eq(po[0].reshape(-1, 32), cpu.x25519(sec, pts), "x25519 from page-locked memory")
+    found["x25519 pinned"] = residue(sec) + residue(po[0].reshape(-1, 32))
+    sim.clean()
+    # public data is NOT wiped (the search is live): signatures stay in the staging slots after a verify
+    ed.ed25519_verify_batch(sig, pub, msgs, None, 20)
+    assert residue(sig) > 0
+    if negative:
+        assert all(v > 0 for v in found.values()), found
+    else:
+        assert all(v == 0 for v in found.values()), found
+    # one device, staging of the last call
+    assert len(ed.peek_staging(0, 0, 64)) == 64
+
+
+def _verify_case(sim, cpu, r, n):
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, max_len=90)
+    bad_sig, bad_pub = mutate(r, sig, pub, 0.2)
+    return bad_sig, bad_pub, msgs, off, cpu.verify(bad_sig, bad_pub, msgs, off, 0)
+
+
+def scenario_failures():
+    """Every runtime call host.c makes fails once, at every position, during a multi-chunk call and during context creation:
+    the call reports the error (never a wrong result), secrets do not linger, nothing leaks, and the next call works."""
+    from cpu_ref import best_cpu_impl, Oracle
+    assert os.environ.get("CUDASIM_SMS") == "1" and os.environ.get("CUDASIM_RESIDENT") == "32"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(7)
+    n = 140
+    vsig, vpub, vmsgs, voff, vwant = _verify_case(sim, cpu, r, n)           # a wave is 32: chunks of 32, 32, 64, 12 — every slot is reused
+    sec = rand_rows(r, 70000)                                               # sk conversion (secret in AND out): chunks of 65536 + 4464
+    ok = np.zeros(n, np.uint8)
+    outs = np.zeros_like(sec)
+    voff64 = np.ascontiguousarray(voff, np.uint64)
+    orc = Oracle()
+
+    def run_verify():
+        ok[:] = 9
+        return L.ed25519_verify_batch(n, ok.ctypes.data, vsig.ctypes.data, vpub.ctypes.data, vmsgs.ctypes.data, voff64.ctypes.data, 0)
+
+    def run_secret():
+        outs[:] = 0
+        return L.sk_ed25519_to_x25519_batch(len(sec), outs.ctypes.data, sec.ctypes.data)
+
+    assert run_secret() == 0
+    want_out = outs.copy()
+    for i in range(0, len(sec), 2003):
+        assert bytes(want_out[i]) == orc.sk_to_x25519(bytes(sec[i]))
+    assert run_verify() == 0 and (ok == vwant).all()
+    tested = lost = 0           # lost: scratch blocks whose cudaFreeAsync was made to fail (nothing the library could do)
+    for fresh_context in (False, True):
+        for api in range(16):
+            nth = 0
+            while True:
+                nth += 1
+                if fresh_context:
+                    ed.shutdown()
+                    assert sim.live()[0] == lost, f"leak after shutdown: {sim.live()} before {API_NAMES[api]} call {nth}"
+                L.cudasim_fail(api, nth)
+                rc_v = run_verify()
+                rc_g = run_secret() if rc_v == 0 else 0
+                where = f"{API_NAMES[api]} call {nth}, fresh context {fresh_context}"
+                if rc_v == 0 and rc_g == 0:
+                    # the failure was not reached (or hit a call whose error is tolerated): results must be right
+                    assert (ok == vwant).all() and (outs == want_out).all(), where
+                    L.cudasim_clear_faults()
+                    assert sim.errors() == 0, sim.first_error()
+                    break
+                tested += 1
+                lost += api == API_FREE_ASYNC
+                assert L.eddsa_b200_last_error() != b"", where
+                assert sim.pending() == 0, f"{where}: {sim.pending()} operations left queued after a failed call"
+                assert L.cudasim_current_device() == 0, where
+                if rc_g:
+                    hits = sim.find([sec[i] for i in range(0, len(sec), 101)] + [want_out[i] for i in range(0, len(sec), 101)])
+                    assert hits == 0, f"{where}: {hits} secret keys left in library buffers after a failed secret-key call"
+                L.cudasim_clear_faults()
+                L.cudasim_clear_errors()        # a faulted run may have tripped bounds checks on poisoned data; start clean
+                assert run_verify() == 0 and (ok == vwant).all(), f"verify after {where}"
+                assert nth < 400, where
+    assert run_secret() == 0 and (outs == want_out).all()
+    sim.clean()
+    assert tested > 60, tested
+    print("failure positions exercised:", tested)
+
+
+def scenario_threads():
+    """Four host threads issue mixed batch and single calls at once (two devices): every result is right."""
+    from cpu_ref import best_cpu_impl
+    sim, cpu = Sim(), best_cpu_impl()
+    ed = sim.ed
+    r = rng(8)
+    cases = []
+    for t in range(4):
+        n = 20000 + 1000 * t
+        sec, pub, msgs, off, sig = make_signed(cpu, r, 1500 + 100 * t, max_len=60)
+        bad_sig, bad_pub = mutate(r, sig, pub, 0.2)
+        a, b = rand_rows(r, n), rand_rows(r, n)
+        cases.append(dict(sec=sec, pub=pub, msgs=msgs, off=off, sig=sig, bad_sig=bad_sig, bad_pub=bad_pub,
+                          want=cpu.verify(bad_sig, bad_pub, msgs, off, 0), a=a, b=b, x=cpu.x25519_base(sec[:300])))
+    errs = []
+
+    def work(c, t):
+        try:
+            for it in range(3):
+                eq(ed.ed25519_verify_batch(c["bad_sig"], c["bad_pub"], c["msgs"], c["off"], 0), c["want"], f"thread {t} verify")
+                eq(ed.ed25519_sign_batch(c["sec"], c["pub"], c["msgs"], c["off"], 0), c["sig"], f"thread {t} sign")
+                check_fe_add(ed.fe_selftest(c["a"], c["b"], 2), c["a"], c["b"], range(0, len(c["a"]), 501))
+                eq(ed.x25519_base_batch(c["sec"][:300]), c["x"], f"thread {t} x25519_base")
+                assert ed.ed25519_genpub(bytes(c["sec"][it])) == bytes(c["pub"][it])
+        except BaseException as e:      # noqa: BLE001 — reported by the main thread
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(c, t)) for t, c in enumerate(cases)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errs, errs
+    sim.clean()
+
+
+def scenario_dev_api():
+    """The device-pointer entry points: asynchronous on the caller's stream, scratch from the pool, argument checks."""
+    from cpu_ref import best_cpu_impl
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(9)
+    n = 2500
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, max_len=70)
+    bad_sig, bad_pub = mutate(r, sig, pub, 0.2)
+    want = cpu.verify(bad_sig, bad_pub, msgs, off, 0)
+    off64 = np.ascontiguousarray(off, np.uint64)
+
+    def dev(arr):
+        a, p = sim.user_array(arr.nbytes + 16, K_DEVICE)           # + 16: the kernels' 128-bit loads may run past the blob
+        a[:arr.nbytes] = arr.view(np.uint8).reshape(-1)
+        return a, p
+
+    d_sig, d_pub, d_msgs, d_off, d_sec = dev(bad_sig), dev(bad_pub), dev(msgs), dev(off64), dev(sec)
+    d_ok, d_out, d_sig2 = sim.user_array(n, K_DEVICE), sim.user_array(32 * n, K_DEVICE), sim.user_array(64 * n, K_DEVICE)
+    s1, s2 = L.cudasim_stream_create(0), L.cudasim_stream_create(0)
+    sim.reset()
+    before = ed.launch_count()
+    assert L.ed25519_verify_batch_dev(n, d_ok[1], d_sig[1], d_pub[1], d_msgs[1], d_off[1], 0, s1) == 0
+    assert L.ed25519_genpub_batch_dev(n, d_out[1], d_sec[1], s2) == 0
+    if os.environ.get("CUDASIM_SCHEDULE", "lazy") == "lazy":
+        assert sim.pending() > 0 and (d_ok[0] == 0xCC).all()         # nothing has run: the calls only enqueue
+    L.cudasim_sync_all()
+    eq(d_ok[0], want, "verify_batch_dev")
+    eq(d_out[0].reshape(-1, 32), pub, "genpub_batch_dev")
+    assert ed.launch_count() - before == 5
+    d_pub2 = dev(pub)
+    assert L.ed25519_sign_batch_dev(n, d_sig2[1], d_sec[1], d_pub2[1], d_msgs[1], d_off[1], 0, None) == 0     # default stream
+    assert L.x25519_base_batch_dev(n, d_out[1], d_sec[1], s1) == 0
+    L.cudasim_sync_all()
+    eq(d_sig2[0].reshape(-1, 64), sig, "sign_batch_dev")
+    eq(d_out[0].reshape(-1, 32), cpu.x25519_base(sec), "x25519_base_batch_dev")
+    assert L.x25519_batch_dev(n, d_out[1], d_sec[1], d_pub2[1], s2) == 0
+    L.cudasim_sync_all()
+    eq(d_out[0].reshape(-1, 32), cpu.x25519(sec, pub), "x25519_batch_dev")
+    assert L.pk_ed25519_to_x25519_batch_dev(n, d_out[1], d_pub2[1], s2) == 0 and L.sk_ed25519_to_x25519_batch_dev(n, d_sig2[1], d_sec[1], s1) == 0
+    L.cudasim_sync_all()
+    eq(d_out[0].reshape(-1, 32), ed.pk_ed25519_to_x25519_batch(pub), "pk conversion, device API vs host API")
+    sim.clean()
+    st = sim.stats()
+    assert st["pool_allocs"] == 3 and st["dev_allocs"] <= 6 + 2, st      # scratch of verify, genpub, sign from the pool
+    # argument checks: nothing launched, EINVAL
+    before = ed.launch_count()
+    assert L.ed25519_verify_batch_dev(n, d_ok[1], d_sig[1] + 8, d_pub[1], d_msgs[1], d_off[1], 0, s1) == EINVAL
+    assert L.ed25519_verify_batch_dev(n, d_ok[1], d_sig[1], None, d_msgs[1], d_off[1], 0, s1) == EINVAL
+    assert L.ed25519_verify_batch_dev(n, d_ok[1], d_sig[1], d_pub[1], None, d_off[1], 0, s1) == EINVAL
+    assert L.ed25519_genpub_batch_dev(n, d_out[1] + 4, d_sec[1], s1) == EINVAL
+    assert L.ed25519_sign_batch_dev(n, d_sig2[1], d_sec[1], None, d_msgs[1], d_off[1], 0, s1) == EINVAL
+    assert L.x25519_batch_dev(n, d_out[1], d_sec[1], None, s1) == EINVAL
+    assert L.ed25519_verify_batch_dev(0, None, None, None, None, None, 0, s1) == 0
+    assert L.ed25519_verify_batch_dev(n - 3, d_ok[1] + 3, d_sig[1], d_pub[1], d_msgs[1], d_off[1], 0, s1) == 0   # the flags: any alignment
+    L.cudasim_sync_all()
+    eq(d_ok[0][3:], want[:-3], "verify flags at an odd address")
+    assert ed.launch_count() == before + 3 and sim.errors() == 0, sim.first_error()
+    # batches larger than a pass reuse one scratch allocation of min(n, pass) records
+    big = 2 * 2 * 512 * 16 + 100                                     # two simulated SMs: a pass is 16384 signatures
+    reps = -(-big // n)
+    t_sig, t_pub = np.tile(bad_sig, (reps, 1))[:big], np.tile(bad_pub, (reps, 1))[:big]
+    fixed = r.integers(0, 256, size=big * 8, dtype=np.uint8)
+    e_sig, e_pub, e_msgs, e_ok = dev(t_sig), dev(t_pub), dev(fixed), sim.user_array(big, K_DEVICE)
+    sim.reset()
+    assert L.ed25519_verify_batch_dev(big, e_ok[1], e_sig[1], e_pub[1], e_msgs[1], None, 8, s2) == 0
+    L.cudasim_sync_all()
+    assert not e_ok[0].any() and sim.stats()["pool_allocs"] == 1
+    sim.clean()
+
+
+def scenario_lifecycle():
+    """init / shutdown / re-initialisation: nothing the library allocated survives a shutdown; the single-operation API and the
+    obsolete aliases (reference eddsa.h:84-114) give the reference's results."""
+    from cpu_ref import best_cpu_impl, Oracle
+    sim, cpu, orc = Sim(), best_cpu_impl(), Oracle()
+    ed, L = sim.ed, sim.L
+    r = rng(10)
+    ed.init()
+    assert ed.device_count() == int(os.environ.get("CUDASIM_DEVICES", "4"))
+    assert sim.live(K_PINNED) == (0, 0)                              # contexts without staging buffers
+    sec, pub, msgs, off, sig = make_signed(cpu, r, 8, max_len=200)
+    for i in range(8):
+        m = bytes(msgs[int(off[i]):int(off[i + 1])])
+        assert ed.ed25519_genpub(bytes(sec[i])) == bytes(pub[i])
+        assert ed.ed25519_sign(bytes(sec[i]), bytes(pub[i]), m) == bytes(sig[i])
+        assert ed.ed25519_verify(bytes(sig[i]), bytes(pub[i]), m)
+        assert not ed.ed25519_verify(bytes(sig[i]), bytes(pub[i]), m + b"x")
+        assert ed.x25519_base(bytes(sec[i])) == bytes(cpu.x25519_base(sec[i:i + 1])[0])
+        assert ed.x25519(bytes(sec[i]), bytes(pub[i])) == bytes(cpu.x25519(sec[i:i + 1], pub[i:i + 1])[0])
+        assert ed.pk_ed25519_to_x25519(bytes(pub[i])) == orc.pk_to_x25519(bytes(pub[i]))
+        assert ed.sk_ed25519_to_x25519(bytes(sec[i])) == orc.sk_to_x25519(bytes(sec[i]))
+    out32, out64 = ctypes.create_string_buffer(32), ctypes.create_string_buffer(64)
+    m0 = bytes(msgs[int(off[0]):int(off[1])])
+    L.eddsa_genpub(out32, bytes(sec[0]))
+    assert out32.raw == bytes(pub[0])
+    L.eddsa_sign(out64, bytes(sec[0]), bytes(pub[0]), m0, ctypes.c_size_t(len(m0)))
+    assert out64.raw == bytes(sig[0])
+    L.eddsa_verify.restype = ctypes.c_bool
+    assert L.eddsa_verify(bytes(sig[0]), bytes(pub[0]), m0, ctypes.c_size_t(len(m0)))
+    L.DH(out32, bytes(sec[0]), bytes(pub[1]))
+    assert out32.raw == bytes(cpu.x25519(sec[0:1], pub[1:2])[0])
+    L.eddsa_pk_eddsa_to_dh(out32, bytes(pub[0]))
+    assert out32.raw == orc.pk_to_x25519(bytes(pub[0]))
+    L.eddsa_sk_eddsa_to_dh(out32, bytes(sec[0]))
+    assert out32.raw == orc.sk_to_x25519(bytes(sec[0]))
+    # NULL data with length 0 is what the reference's callers pass for an empty message
+    L.ed25519_sign(out64, bytes(sec[0]), bytes(pub[0]), None, 0)
+    assert out64.raw == bytes(cpu.sign(sec[0:1], pub[0:1], np.zeros(1, np.uint8), None, 0)[0])
+    assert L.ed25519_verify(out64.raw, bytes(pub[0]), None, 0)
+    sim.clean()
+    for round_ in range(3):
+        assert sim.live()[0] > 0
+        ed.shutdown()
+        assert sim.live() == (0, 0) and sim.pending() == 0, sim.live()
+        ed.shutdown()                                                # twice is harmless
+        eq(ed.ed25519_genpub_batch(sec), pub, "genpub after a shutdown")
+    # the tables the kernels read, through the diagnostic readers (checked against the big-integer model by test_host_sim)
+    import edmodel as em
+    em.check_comb_table(ed.comb_table(), 6)
+    t = ed.verify_tables()
+    assert t.shape == (2, 32769, 3, 32) and not t[0, 0, 2].any()
+    sim.clean()
+
+
+def scenario_no_device():
+    """No usable device: the batch calls report it (there is no CPU path to fall back to)."""
+    assert os.environ.get("CUDASIM_DEVICES") == "0"
+    sim = Sim()
+    L = sim.L
+    buf = np.zeros(64, np.uint8)
+    assert L.ed25519_genpub_batch(2, buf.ctypes.data, buf.ctypes.data) == 100          # cudaErrorNoDevice
+    assert b"no usable CUDA device" in L.eddsa_b200_last_error()
+    assert L.ed25519_verify_batch_dev(2, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, buf.ctypes.data, None, 4, None) == 100
+    assert L.eddsa_b200_init() == 100 and L.eddsa_b200_device_count() == 0
+    L.eddsa_b200_shutdown()
+    if len(sys.argv) > 2 and sys.argv[2] == "abort":
+        out = ctypes.create_string_buffer(32)
+        L.ed25519_genpub(out, bytes(32))                             # void function, cannot report: must abort()
+        print("NOT REACHED")
+
+
+SCENARIOS = {k[len("scenario_"):]: v for k, v in list(globals().items()) if k.startswith("scenario_")}
+
+if __name__ == "__main__":
+    SCENARIOS[sys.argv[1]]()
+    print("OK", sys.argv[1])

@@ -1,0 +1,129 @@
+"""The host layer (libeddsa_b200/csrc/host.c: sharding over devices, worker threads, chunk schedule, staging slots, event
+dependencies, scrubbing of secrets, error paths, the single-operation API) exercised WITHOUT a GPU: host.c is linked, unchanged,
+against a simulator of the CUDA runtime (tests/host_sim/cudasim.cpp — lazily executing streams, bounds-checked memory, failure
+injection; its "kernels" run the per-thread operation bodies of ops.cuh compiled for the host) and driven through the product's
+own ctypes binding.  Every scenario (tests/host_sim/sim_scenarios.py) runs in a fresh interpreter and checks results against the
+CPU reference.  This is test infrastructure only: the simulator lives under tests/ and the product has no CPU path.
+
+The mutants at the end prove the simulator has teeth: host.c with one dependency, synchronisation or scrub removed must FAIL the
+scenario that covers it.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HS = os.path.join(HERE, "host_sim")
+HOST_C = os.path.join(os.path.dirname(HERE), "libeddsa_b200", "csrc", "host.c")
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    subprocess.run(["make", "-s", "-C", HS], check=True)
+    return os.path.join(HS, "libeddsa_sim.so")
+
+
+def run_scenario(name, env=None, args=(), so=None, timeout=600):
+    e = {k: v for k, v in os.environ.items() if not k.startswith(("CUDASIM_", "EDDSA_B200_"))}
+    e.update(env or {})
+    if so:
+        e["CUDASIM_SO"] = so
+    return subprocess.run([sys.executable, os.path.join(HS, "sim_scenarios.py"), name, *args], env=e, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, text=True, timeout=timeout)
+
+
+SCENARIOS = {
+    "all_ops": {"CUDASIM_DEVICES": "1"},
+    "chunks": {"CUDASIM_DEVICES": "1", "CUDASIM_SMS": "1"},
+    "budget": {"CUDASIM_DEVICES": "1", "EDDSA_B200_CHUNK_MB": "1"},
+    "multi": {"CUDASIM_DEVICES": "4"},
+    "device_list": {"CUDASIM_DEVICES": "4", "EDDSA_B200_DEVICES": "2,0"},
+    "scrub": {"CUDASIM_DEVICES": "1"},
+    "failures": {"CUDASIM_DEVICES": "1", "CUDASIM_SMS": "1", "CUDASIM_RESIDENT": "32"},
+    "threads": {"CUDASIM_DEVICES": "2"},
+    "dev_api": {"CUDASIM_DEVICES": "1"},
+    "lifecycle": {"CUDASIM_DEVICES": "4"},
+    "no_device": {"CUDASIM_DEVICES": "0"},
+}
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_host_layer_on_the_simulator(simlib, name):
+    """Lazy streams: an operation runs only when something waits for it — the most adversarial legal schedule."""
+    res = run_scenario(name, SCENARIOS[name])
+    assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
+
+
+@pytest.mark.parametrize("schedule", ["others-first", "eager", "random"])
+@pytest.mark.parametrize("name", ["chunks", "budget", "multi", "threads", "dev_api", "failures"])
+def test_host_layer_under_other_schedules(simlib, name, schedule):
+    if name == "failures" and schedule != "others-first":
+        pytest.skip("the failure sweep runs under the two adversarial schedules only (12 s each)")
+    """The same scenarios with every other stream running as far as it can before the awaited one advances (work without a
+    dependency runs EARLY — the complement of the lazy schedule), with everything executing at once, and with a random
+    interleaving of the streams."""
+    res = run_scenario(name, dict(SCENARIOS[name], CUDASIM_SCHEDULE=schedule))
+    assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
+
+
+def test_scrub_negative_control(simlib):
+    """With the scrubbing switched off the same search finds the secrets: the scrub is what removes them."""
+    res = run_scenario("scrub", dict(SCENARIOS["scrub"], EDDSA_B200_DEBUG_NO_SCRUB="1"))
+    assert res.returncode == 0 and "OK scrub" in res.stdout, res.stdout[-3000:]
+
+
+def test_single_operation_without_a_device_aborts(simlib):
+    """The void functions of eddsa.h cannot report an error and there is no CPU fallback: they abort."""
+    res = run_scenario("no_device", SCENARIOS["no_device"], args=("abort",))
+    assert res.returncode == -6 and "NOT REACHED" not in res.stdout and "no usable CUDA device" in res.stdout, (res.returncode, res.stdout[-2000:])
+
+
+# (what is removed from host.c, the exact text, its replacement, the scenario that must notice)
+MUTANTS = [
+    ("kernels do not wait for their chunk's input copies",
+     "            CU(cudaStreamWaitEvent(c->kstream, c->in_ready[s], 0));\n", "", "chunks"),
+    ("the result copy does not wait for the kernels",
+     "            CU(cudaStreamWaitEvent(c->stream[s], c->k_done[s], 0));\n", "", "chunks"),
+    ("a slot is reused without waiting for the chunk that used it",
+     "        if (slot[s].inflight) { /* retire the chunk that used this slot */\n            CU(cudaEventSynchronize(c->done[s]));\n",
+     "        if (slot[s].inflight) { /* retire the chunk that used this slot */\n", "chunks"),
+    ("the last chunks are handed out without waiting for them",
+     "            cudaError_t e = rc ? cudaSuccess : cudaEventSynchronize(c->done[s]);\n", "            cudaError_t e = cudaSuccess;\n", "all_ops"),
+    ("buffers are re-allocated while chunks are in flight",
+     "                if (slot[k].inflight) {\n                    CU(cudaEventSynchronize(c->done[k]));\n                    retire_slot(c, j, &slot[k], k, pin_out, 1);\n                }\n",
+     "                slot[k].inflight = 0;\n", "budget"),
+    ("message offsets are not rebased to the chunk",
+     "ho[i] = (unsigned long long)(j->off[pos + i] - j->off[pos]);", "ho[i] = (unsigned long long)j->off[pos + i];", "budget"),
+    ("the device copy of the secret keys is not wiped",
+     "        if (secret_in) CU(cudaMemsetAsync(c->d_in[s], 0, m * j->in_item[0], c->stream[s]));", "", "scrub"),
+    ("the staged host copy of the secret keys is not wiped",
+     "    if (sl->staged_secret && !g_no_scrub) memset(c->h_in[s], 0, m * j->in_item[0]);\n", "", "scrub"),
+    ("secret outputs stay in the host slot",
+     "        if (op_secret_out(j->op) && !g_no_scrub) memset(c->h_out[s], 0, m * j->out_item);\n", "", "scrub"),
+    ("the caller's current device is not restored",
+     "    if (prev_dev >= 0 && prev_dev != c->dev) cudaSetDevice(prev_dev);\n", "", "multi"),
+    ("a failed call returns while chunks are still in flight",
+     "                cudaDeviceSynchronize();        /* the younger chunks", "                ;        /* the younger chunks", "failures"),
+    ("keys staged by the chunk that failed are not wiped",
+     "            if (c->h_in[k]) memset(c->h_in[k], 0, c->in_cap);\n", "", "failures"),
+    ("shards overlap by one item",
+     "        sh[g].hi = j->n * (size_t)(g + 1) / ndev;", "        sh[g].hi = j->n * (size_t)(g + 1) / ndev + (g + 1 < ndev);", "multi"),
+]
+
+
+@pytest.mark.parametrize("what,old,new,scenario", MUTANTS, ids=[m[0] for m in MUTANTS])
+def test_simulator_catches_host_layer_mutants(simlib, tmp_path, what, old, new, scenario):
+    src = open(HOST_C).read()
+    assert src.count(old) == 1, f"host.c changed: the text of mutant '{what}' must occur exactly once"
+    mutant_c, so = tmp_path / "host.c", tmp_path / "libeddsa_sim_mutant.so"
+    mutant_c.write_text(src.replace(old, new))
+    inc = ["-I" + os.path.join(os.path.dirname(HERE), "include"), "-I" + os.path.join(os.path.dirname(HOST_C)), "-I/usr/local/cuda/include"]
+    subprocess.run(["gcc", "-O2", "-std=gnu11", "-fPIC", "-fvisibility=hidden", "-DEDDSA_BUILD", *inc, "-c", str(mutant_c), "-o", str(tmp_path / "host.o")], check=True)
+    subprocess.run(["g++", "-shared", "-o", str(so), os.path.join(HS, "cudasim.o"), str(tmp_path / "host.o"), "-lpthread"], check=True)
+    for schedule in ("lazy", "others-first"):
+        res = run_scenario(scenario, dict(SCENARIOS[scenario], CUDASIM_SCHEDULE=schedule), so=str(so))
+        if res.returncode != 0:
+            return
+    raise AssertionError(f"the '{scenario}' scenario did not notice that {what}")
