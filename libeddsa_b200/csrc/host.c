@@ -343,7 +343,8 @@ static struct {
 static void *copy_helper(void *arg)
 {
     const size_t k = (size_t)(uintptr_t)arg;           /* helper k copies slice k + 1 (the caller takes slice 0) */
-    unsigned long seen = 0;
+    unsigned long seen = 0;                            /* helpers are created under g_copy.m by the call that posts their first
+                                                        * request, so whatever generation they see first is a live request */
     for (;;) {
         pthread_mutex_lock(&g_copy.m);
         while (g_copy.gen == seen && !g_copy.stop) pthread_cond_wait(&g_copy.go, &g_copy.m);

@@ -195,6 +195,17 @@ def scenario_all_ops():
     sec, pub, msgs, off, sig = make_signed(cpu, r, 5, fixed_len=0)
     eq(ed.ed25519_sign_batch(sec, pub, None, None, 0), sig, "sign of empty messages")
     assert ed.ed25519_verify_batch(sig, pub, None, None, 0).all()
+    # offsets that do not start at zero, and a ragged batch whose messages are all empty
+    sec, pub, msgs, off, sig = make_signed(cpu, r, 50, max_len=33)
+    shifted = np.concatenate([rand_rows(r, 1, 13).reshape(-1), msgs])
+    off13 = off + np.uint64(13)
+    eq(ed.ed25519_sign_batch(sec, pub, shifted, off13, 0), sig, "sign with offsets starting at 13")
+    assert ed.ed25519_verify_batch(sig, pub, shifted, off13, 0).all()
+    zero_off = np.full(51, 7, np.uint64)
+    empty_sig = cpu.sign(sec, pub, shifted, zero_off, 0)
+    eq(ed.ed25519_sign_batch(sec, pub, shifted, zero_off, 0), empty_sig, "ragged sign of empty messages")
+    assert ed.ed25519_verify_batch(empty_sig, pub, shifted, zero_off, 0).all()
+    sim.clean()
     # argument errors: EINVAL, a message, nothing launched
     L = sim.L
     before = ed.launch_count()
@@ -355,6 +366,15 @@ def scenario_multi():
     sim.clean()
     assert {d for d, _, _ in sim.launches(L_VERIFY)} == {0, 1, 2, 3}
     assert L.cudasim_current_device() == 3
+    # one shard fails (an allocation on whichever device asks third): the call reports it, the next call is fine
+    ed.shutdown()
+    L.cudasim_fail(API_MALLOC_HOST, 3)
+    ok, off64 = np.zeros(n, np.uint8), np.ascontiguousarray(off, np.uint64)
+    assert L.ed25519_verify_batch(n, ok.ctypes.data, bad_sig.ctypes.data, bad_pub.ctypes.data, msgs.ctypes.data, off64.ctypes.data, 0) == 2   # cudaErrorMemoryAllocation
+    assert b"cudaMallocHost" in L.eddsa_b200_last_error() and sim.pending() == 0
+    L.cudasim_clear_faults()
+    eq(ed.ed25519_verify_batch(bad_sig, bad_pub, msgs, off, 0), cpu.verify(bad_sig, bad_pub, msgs, off, 0), "verify after a failed shard")
+    sim.clean()
     # a single operation runs on the first configured device and leaves the caller's device alone
     sim.reset()
     assert ed.ed25519_verify(bytes(sig[0]), bytes(pub[0]), bytes(msgs[int(off[0]):int(off[1])]))
@@ -662,6 +682,27 @@ def scenario_lifecycle():
     t = ed.verify_tables()
     assert t.shape == (2, 32769, 3, 32) and not t[0, 0, 2].any()
     sim.clean()
+
+
+def scenario_copy_helpers():
+    """Staging copies of 8 MB and more are split over helper threads (EDDSA_B200_COPY_THREADS=3); the helpers are stopped by a
+    shutdown and re-created afterwards without replaying the last request of their predecessors."""
+    assert os.environ.get("EDDSA_B200_COPY_THREADS") == "3"
+    sim = Sim()
+    ed = sim.ed
+    r = rng(11)
+    n = 1200000
+    for round_ in range(3):
+        a, b = rand_rows(r, n), rand_rows(r, n)
+        sim.reset()
+        out = ed.fe_selftest(a, b, 2)
+        check_fe_add(out, a, b, list(range(0, n, 4001)) + [65535, 65536, 65536 + 262143, 65536 + 262144, n - 1])
+        sim.clean()
+        sizes = [x[2] for x in sim.launches(L_FE_TEST)]
+        assert sizes[:3] == [65536, 262144, 300000] and sum(sizes) == n, sizes      # 262144 x 32 bytes = 8 MB: the helpers' threshold
+        del a, b, out
+        ed.shutdown()
+        assert sim.live() == (0, 0)
 
 
 def scenario_no_device():

@@ -45,6 +45,7 @@ SCENARIOS = {
     "threads": {"CUDASIM_DEVICES": "2"},
     "dev_api": {"CUDASIM_DEVICES": "1"},
     "lifecycle": {"CUDASIM_DEVICES": "4"},
+    "copy_helpers": {"CUDASIM_DEVICES": "1", "EDDSA_B200_COPY_THREADS": "3"},
     "no_device": {"CUDASIM_DEVICES": "0"},
 }
 
