@@ -95,7 +95,7 @@ EDDSA_DECL int eddsa_b200_sc_selftest(size_t n, uint8_t *out, const uint8_t *a, 
  * elements).  Returns the number of bytes written (2 x 32769 x 96) or 0 if `cap` is too small / on error. */
 EDDSA_DECL size_t eddsa_b200_verify_tables(uint8_t *out, size_t cap);
 /* diagnostic: copies the fixed-base comb table of the current device to `out`: rows x entries x 96 bytes, entry
- * [j][k] = (k + 1) * 2^(W j) * B as (y+x, y-x, 2dxy) (W = 5: 51 rows x 16 entries).  Returns the bytes written or 0. */
+ * [j][k] = (k + 1) * 2^(W j) * B as (y+x, y-x, 2dxy) (W = 6: 43 rows x 32 entries).  Returns the bytes written or 0. */
 EDDSA_DECL size_t eddsa_b200_comb_table(uint8_t *out, size_t cap);
 /* diagnostic (tests of the secret-scrubbing contract): copies up to `len` bytes from the start of staging buffer
  * `which` (0 host input, 1 device input, 2 host output, 3 device output) of pipeline slot `slot` (0..2) of the
