@@ -705,6 +705,141 @@ def scenario_copy_helpers():
         assert sim.live() == (0, 0)
 
 
+def scenario_fuzz():
+    """A random walk over the C-ABI: random operations, sizes, message layouts, page-locked / ordinary buffers, device counts,
+    caller devices, shutdowns and injected runtime failures (seed: argv[2]).  Every successful call is checked against the
+    CPU reference; every failed call must leave nothing queued, no secret behind, and a working library."""
+    import hashlib
+    from cpu_ref import best_cpu_impl
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 60
+    assert os.environ.get("CUDASIM_RESIDENT") == "32" and os.environ.get("CUDASIM_SMS") == "1"      # a verify wave is 32 signatures
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(1000 + seed)
+    ndev = ed.device_count()
+    pool = make_signed(cpu, r, 700, max_len=120)                     # material for sign / verify calls
+    psec, ppub, pmsgs, poff, psig = pool
+    log, lost_blocks = [], 0       # lost: scratch blocks whose cudaFreeAsync was made to fail (they stay allocated for good)
+
+    def buf(arr, pinned):
+        """The array as the caller's buffer: ordinary numpy memory or memory the simulator knows as page-locked."""
+        arr = np.ascontiguousarray(arr)
+        if not pinned:
+            return arr, arr.ctypes.data, None
+        a, p = sim.user_array(arr.nbytes, K_PINNED)
+        a[:] = arr.view(np.uint8).reshape(-1)
+        return a, p, p
+
+    def sk_expected(sec):
+        out = np.zeros_like(sec)
+        for i, k in enumerate(sec):
+            h = bytearray(hashlib.sha512(bytes(k)).digest()[:32])
+            h[0] &= 248
+            h[31] = (h[31] & 127) | 64
+            out[i] = np.frombuffer(bytes(h), np.uint8)
+        return out
+
+    for step in range(steps):
+        what = r.choice(["fe_add", "fe_add", "sk_conv", "sk_conv", "verify", "verify", "sign", "x25519_base", "shutdown", "devices"])
+        if what == "shutdown":
+            ed.shutdown()
+            assert sim.live()[0] == lost_blocks, (step, sim.live(), lost_blocks)
+            continue
+        if what == "devices":
+            ed.set_device_count(int(r.integers(0, ndev + 1)))
+            continue
+        caller_dev = int(r.integers(0, ndev))
+        L.cudasim_set_device(caller_dev)
+        fail_api, fail_nth = (int(r.integers(0, 16)), int(r.integers(1, 25))) if r.random() < 0.3 else (-1, 0)
+        if fail_api == API_SET_DEVICE:
+            fail_nth = 1            # a later cudaSetDevice is the one that RESTORES the caller's device: nothing could be done about that
+        pins = [bool(r.integers(0, 2)) for _ in range(5)]
+        frees, secrets = [], []
+        if what == "fe_add":
+            n = int(r.choice([0, 1, 777, 16384, 16385, 65537, 150001]))
+            a, b = rand_rows(r, n), rand_rows(r, n)
+            (A, pa, fa), (B, pb, fb), (O, po, fo) = buf(a, pins[0]), buf(b, pins[1]), buf(np.zeros_like(a), pins[2])
+            frees += [fa, fb, fo]
+            call = lambda: L.eddsa_b200_fe_selftest(n, po, pa, pb, 2)
+            check = lambda: check_fe_add(O.reshape(-1, 32), a, b, sorted(set(int(x) for x in r.integers(0, n, 60))) + [0, n - 1] if n else [])
+        elif what == "sk_conv":
+            n = int(r.choice([1, 33, 5000, 16385, 70001]))
+            sec = rand_rows(r, n)
+            want = sk_expected(sec)
+            (S, ps, fs), (O, po, fo) = buf(sec, pins[0]), buf(np.zeros_like(sec), pins[1])
+            frees += [fs, fo]
+            secrets = [sec[i] for i in range(0, n, max(1, n // 40))] + [want[i] for i in range(0, n, max(1, n // 40))]
+            call = lambda: L.sk_ed25519_to_x25519_batch(n, po, ps)
+            check = lambda: eq(O.reshape(-1, 32), want, "sk conversion")
+        elif what == "x25519_base":
+            n = int(r.choice([1, 40, 300]))
+            sec = rand_rows(r, n)
+            want = cpu.x25519_base(sec)
+            (S, ps, fs), (O, po, fo) = buf(sec, pins[0]), buf(np.zeros_like(sec), pins[1])
+            frees += [fs, fo]
+            secrets = [sec[i] for i in range(0, n, 7)]
+            call = lambda: L.x25519_base_batch(n, po, ps)
+            check = lambda: eq(O.reshape(-1, 32), want, "x25519_base")
+        else:
+            n = int(r.choice([1, 31, 32, 33, 100, 257, 700]))
+            lo = int(r.integers(0, 700 - n + 1))
+            sec, pub, sig = psec[lo:lo + n], ppub[lo:lo + n], psig[lo:lo + n]
+            if r.random() < 0.5:                                     # ragged, offsets not starting at zero
+                off = np.ascontiguousarray(poff[lo:lo + n + 1], np.uint64)
+                msgs, fixed = pmsgs, 0
+                (OFF, poffp, foff) = buf(off, False)
+                want_sig = sig
+            else:
+                fixed = int(r.choice([0, 1, 64, 200]))
+                msgs, off, poffp = r.integers(0, 256, size=max(1, n * fixed), dtype=np.uint8), None, None
+                want_sig = cpu.sign(sec, pub, msgs, None, fixed)
+            (M, pm, fm) = buf(msgs, pins[3])
+            frees += [fm]
+            if what == "sign":
+                (S, ps, fs), (P_, pp, fp), (O, po, fo) = buf(sec, pins[0]), buf(pub, pins[1]), buf(np.zeros((n, 64), np.uint8), pins[2])
+                frees += [fs, fp, fo]
+                secrets = [sec[i] for i in range(0, n, 9)]
+                call = lambda: L.ed25519_sign_batch(n, po, ps, pp, pm, poffp, fixed)
+                check = lambda: eq(O.reshape(-1, 64), want_sig, "sign")
+            else:
+                bad_sig, bad_pub = mutate(r, want_sig, pub, 0.25)
+                want = cpu.verify(bad_sig, bad_pub, msgs, off, fixed)
+                (S, ps, fs), (P_, pp, fp), (O, po, fo) = buf(bad_sig, pins[0]), buf(bad_pub, pins[1]), buf(np.full(n, 7, np.uint8), pins[2])
+                frees += [fs, fp, fo]
+                call = lambda: L.ed25519_verify_batch(n, po, ps, pp, pm, poffp, fixed)
+                check = lambda: eq(O, want, "verify")
+        log.append((step, what, n, pins, fail_api, fail_nth))
+        if fail_api >= 0:
+            L.cudasim_fail(fail_api, fail_nth)
+        rc = call()
+        where = f"seed {seed} step {step}: {log[-1]}"
+        lost = fail_api == API_FREE_ASYNC and rc != 0
+        if rc == 0:
+            check()
+            L.cudasim_clear_faults()
+            assert sim.errors() == 0, where + " " + sim.first_error()
+        else:
+            assert fail_api >= 0 and L.eddsa_b200_last_error() != b"", where
+            if secrets:
+                assert sim.find(secrets) == 0, where + ": secrets left behind by a failed call"
+            L.cudasim_clear_faults()
+            L.cudasim_clear_errors()
+            assert call() == 0, where + " (retry)"
+            check()
+        assert sim.pending() == 0, where
+        assert L.cudasim_current_device() == caller_dev, where
+        if secrets and os.environ.get("EDDSA_B200_DEBUG_NO_SCRUB") != "1":
+            assert sim.find(secrets) == 0, where + ": secrets left behind"
+        for p in frees:
+            if p:
+                L.cudasim_user_free(p)
+        lost_blocks += bool(lost)
+    ed.shutdown()
+    assert sim.live()[0] == lost_blocks, (sim.live(), lost_blocks)
+    print("steps:", len(log), "failures injected:", sum(1 for x in log if x[4] >= 0))
+
+
 def scenario_no_device():
     """No usable device: the batch calls report it (there is no CPU path to fall back to)."""
     assert os.environ.get("CUDASIM_DEVICES") == "0"

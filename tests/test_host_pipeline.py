@@ -69,6 +69,17 @@ def test_host_layer_under_other_schedules(simlib, name, schedule):
     assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
 
 
+@pytest.mark.parametrize("seed,schedule,devices", [(1, "lazy", 3), (2, "others-first", 4), (3, "random", 2), (6, "lazy", 3)])
+def test_random_walk_over_the_c_abi(simlib, seed, schedule, devices):
+    """Random operations, sizes, layouts, page-locked / ordinary buffers, device counts, shutdowns and injected failures
+    (tools/host_fuzz_campaign.sh runs the long version: 240 runs x 100 steps, profiles/r02_notes.md)."""
+    env = {"CUDASIM_DEVICES": str(devices), "CUDASIM_SMS": "1", "CUDASIM_RESIDENT": "32", "CUDASIM_SCHEDULE": schedule}
+    if seed % 3 == 0:
+        env["EDDSA_B200_CHUNK_MB"] = "1"
+    res = run_scenario("fuzz", env, args=(str(seed), "60"))
+    assert res.returncode == 0 and "OK fuzz" in res.stdout, res.stdout[-3000:]
+
+
 def test_scrub_negative_control(simlib):
     """With the scrubbing switched off the same search finds the secrets: the scrub is what removes them."""
     res = run_scenario("scrub", dict(SCENARIOS["scrub"], EDDSA_B200_DEBUG_NO_SCRUB="1"))
