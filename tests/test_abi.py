@@ -69,10 +69,16 @@ def test_no_cpu_fallback_without_device(libpath):
 
 
 def test_product_does_not_reference_oracle():
-    """Nothing under libeddsa_b200/ may import, include or link the oracle."""
+    """Nothing under libeddsa_b200/ may import, include or link the oracle — or the test-only host builds and the CUDA
+    runtime simulator of tests/host_sim — and the shipped library contains no simulator symbol."""
     pkg = os.path.join(ROOT, "libeddsa_b200")
     for dp, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".c", ".cu", ".cuh", ".h", ".inc", "Makefile", ".map")):
-                text = open(os.path.join(dp, f), errors="replace").read()
-                assert "oracle" not in text.lower(), (dp, f)
+                text = open(os.path.join(dp, f), errors="replace").read().lower()
+                assert "oracle" not in text, (dp, f)
+                assert "cudasim" not in text and "libeddsa_sim" not in text, (dp, f)
+    so = os.path.join(pkg, "libeddsa_b200.so")
+    if os.path.exists(so):
+        syms = subprocess.run(["nm", "-D", "--defined-only", so], stdout=subprocess.PIPE, text=True, check=True).stdout
+        assert "cudasim" not in syms
