@@ -80,6 +80,25 @@ def test_random_walk_over_the_c_abi(simlib, seed, schedule, devices):
     assert res.returncode == 0 and "OK fuzz" in res.stdout, res.stdout[-3000:]
 
 
+def test_host_layer_under_sanitizers(simlib, tmp_path):
+    """host.c, the simulator and the host build of the operation bodies compiled with AddressSanitizer + UBSan: no invalid access
+    (a caller buffer written after the call returned would show up here), no undefined arithmetic."""
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan is not installed")
+    root = os.path.dirname(HERE)
+    san = ["-g", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fPIC"]
+    inc = ["-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include"]
+    so = str(tmp_path / "libeddsa_sim_san.so")
+    subprocess.run(["gcc", *san, "-std=gnu11", "-fvisibility=hidden", "-DEDDSA_BUILD", *inc, "-c", HOST_C, "-o", str(tmp_path / "host.o")], check=True)
+    subprocess.run(["g++", *san, "-std=c++17", "-Wno-unknown-pragmas", *inc, "-c", os.path.join(HS, "cudasim.cpp"), "-o", str(tmp_path / "cudasim.o")], check=True)
+    subprocess.run(["g++", "-shared", "-fsanitize=address,undefined", "-o", so, str(tmp_path / "cudasim.o"), str(tmp_path / "host.o"), "-lpthread"], check=True)
+    for name in ("all_ops", "budget"):
+        env = dict(SCENARIOS[name], LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+        res = run_scenario(name, env, so=so)
+        assert res.returncode == 0 and f"OK {name}" in res.stdout and "runtime error" not in res.stdout, res.stdout[-3000:]
+
+
 def test_scrub_negative_control(simlib):
     """With the scrubbing switched off the same search finds the secrets: the scrub is what removes them."""
     res = run_scenario("scrub", dict(SCENARIOS["scrub"], EDDSA_B200_DEBUG_NO_SCRUB="1"))
