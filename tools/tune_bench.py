@@ -22,6 +22,15 @@ r["sign"] = t(lambda: ed.ed25519_sign_batch_dev(sig, sec, pub, msg, fixed_len=64
 r["verify"] = t(lambda: ed.ed25519_verify_batch_dev(ok, sig, pub, msg, fixed_len=64)); r["ok"] = bool(ok.all().item())
 r["x25519"] = t(lambda: ed.x25519_batch_dev(out, sec, pts))
 r["x25519_base"] = t(lambda: ed.x25519_base_batch_dev(out, sec))
+if os.environ.get("TUNE_1KB"):                    # 1 KB messages (BASELINE config 5's shape), 2^18 operations
+    M = 1 << 18
+    big = torch.randint(0, 256, (M, 1024), dtype=torch.uint8, device=dev, generator=g)
+    N_, N = N, M
+    r["sign_1kb"] = t(lambda: ed.ed25519_sign_batch_dev(sig[:M], sec[:M], pub[:M], big, fixed_len=1024))
+    r["verify_1kb"] = t(lambda: ed.ed25519_verify_batch_dev(ok[:M], sig[:M], pub[:M], big, fixed_len=1024)); r["ok_1kb"] = bool(ok[:M].all().item())
+    r["chk_1kb"] = int(sig[:M].to(torch.int64).sum().item())
+    N = N_
+    ed.ed25519_sign_batch_dev(sig, sec, pub, msg, fixed_len=64)
 chk = int(out.to(torch.int64).sum().item()) ^ int(sig.to(torch.int64).sum().item())
 r["chk"] = chk
 print(json.dumps(r), flush=True)
