@@ -5,6 +5,10 @@
 #include <stdint.h>
 #define EDG_COUNT_OPS
 #include "../../libeddsa_b200/csrc/ops.cuh"
+#if defined(__CUDA_ARCH__)   // PTX-emulation build (ptx_rewrite.py + ptx_emul.h): the device paths carry no instrumentation
+static unsigned long edg_cnt_mul = 0, edg_cnt_sq = 0;
+static int edg_last_nwin = 0;
+#endif
 using namespace edg;
 // the fixed-base comb table, built exactly as the device does (k_comb_base / k_comb_rows); not counted as field work
 static const u32 *host_comb() {
@@ -114,6 +118,17 @@ int hs_verify_full(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, u
     return (int)ed25519_verify_op(s, p, msg, len, qtab, host_wtab(), true);
 }
 int hs_last_nwin(void) { return edg_last_nwin; }
+#if defined(__CUDA_ARCH__)
+// PTX-emulation build only: the verify loop with its cp.async staging of the window's two scratch-table entries through
+// "shared memory" (what k_verify does with s_stage), as thread 0 of a block of one
+int hs_verify_staged(const uint8_t *sig, const uint8_t *pub, const uint8_t *msg, uint64_t len) {
+    u32 s[16], p[8], qtab[EDG_VSTATE_WORDS];
+    static uint4 stage[16];
+    memcpy(s, sig, 64); memcpy(p, pub, 32);
+    ed25519_verify_front(qtab, s, p, msg, len, false);
+    return (int)ed25519_verify_loop(qtab, host_wtab(), reinterpret_cast<u32 *>(stage));
+}
+#endif
 void hs_half_gcd(uint32_t *rho_abs, uint32_t *rho_neg, uint32_t *tau, const uint32_t *t) { u32 n; half_gcd(rho_abs, n, tau, t); *rho_neg = n; }
 void hs_counts(unsigned long *mul, unsigned long *sq, int reset) { *mul = edg_cnt_mul; *sq = edg_cnt_sq; if (reset) edg_cnt_mul = edg_cnt_sq = 0; }
 }

@@ -8,6 +8,7 @@ import hashlib
 import os
 import random
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -16,23 +17,44 @@ import golden_util as gu
 from edmodel import L, P
 
 HS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_sim")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 A8 = ctypes.c_uint32 * 8
 
 
-def _build(name):
-    src, so = os.path.join(HS, name + ".cpp"), os.path.join(HS, "lib" + name + ".so")
-    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
-    return ctypes.CDLL(so)
+def _build(name, flavour="host"):
+    """flavour "host": the portable host paths of the headers.  flavour "device": the DEVICE paths (everything under
+    `#if defined(__CUDA_ARCH__)` — PTX carry chains, funnel shifts, byte permutes, 128-bit loads, cp.async staging), with
+    the inline PTX rewritten into calls of a PTX interpreter (host_sim/ptx_rewrite.py, ptx_emul.h), one lane per call."""
+    src = os.path.join(HS, name + ".cpp")
+    if flavour == "host":
+        so = os.path.join(HS, "lib" + name + ".so")
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, src], check=True)
+    else:
+        gen = os.path.join(HS, "_ptx")
+        os.makedirs(os.path.join(gen, "tests", "host_sim"), exist_ok=True)
+        subprocess.run([sys.executable, os.path.join(HS, "ptx_rewrite.py"), os.path.join(ROOT, "libeddsa_b200", "csrc"),
+                        os.path.join(gen, "libeddsa_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+        gsrc = os.path.join(gen, "tests", "host_sim", name + ".cpp")
+        with open(gsrc, "w") as f:
+            f.write(open(src).read())
+        so = os.path.join(HS, "lib" + name + "_ptx.so")
+        # -fno-gnu-unique: the interpreter's per-statement programs are static locals of inline functions; as GNU_UNIQUE
+        # symbols they would be shared by every library of the process that contains the same function
+        subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-D__CUDA_ARCH__=1000",
+                        "-D__CUDACC__", "-include", os.path.join(HS, "ptx_emul.h"), "-o", so, gsrc], check=True)
+    lib = ctypes.CDLL(so)
+    lib.device_paths = flavour == "device"
+    return lib
 
 
-@pytest.fixture(scope="module")
-def fe():
-    return _build("fe_host")
+@pytest.fixture(scope="module", params=["host", "device"])
+def fe(request):
+    return _build("fe_host", request.param)
 
 
-@pytest.fixture(scope="module")
-def ops():
-    return _build("ops_host")
+@pytest.fixture(scope="module", params=["host", "device"])
+def ops(request):
+    return _build("ops_host", request.param)
 
 
 def val(words):
@@ -191,7 +213,11 @@ def test_ops_adversarial_verify(ops):
     for i in list(range(0, len(sig), 11)) + [i for i in range(len(sig)) if cls[i] >= 16][::3]:
         got = ops.hs_verify_full(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
         assert got == expect[i], (i, int(cls[i]))
-        assert 56 <= ops.hs_last_nwin() <= 64
+        assert ops.device_paths or 56 <= ops.hs_last_nwin() <= 64
+    if ops.device_paths:       # the loop with its cp.async staging through shared memory, as k_verify runs it
+        for i in list(range(0, len(sig), 7)) + [i for i in range(len(sig)) if cls[i] >= 16][::2]:
+            got = ops.hs_verify_staged(sig[i].tobytes(), pub[i].tobytes(), msgs[i], ctypes.c_uint64(len(msgs[i])))
+            assert got == expect[i], (i, int(cls[i]))
 
 
 def wtab_expected(m, e):
@@ -309,6 +335,8 @@ def test_batch_inversion(ops):
             for j, v in enumerate(vals):
                 got = int.from_bytes(buf.raw[32 * j:32 * j + 32], "little")
                 assert got == pow(v % P, P - 2, P), (cnt, j)
+    if ops.device_paths:
+        return                  # the operation counters are host-path instrumentation
     m, s = ctypes.c_ulong(), ctypes.c_ulong()
     ops.hs_counts(ctypes.byref(m), ctypes.byref(s), 1)
     buf = ctypes.create_string_buffer(b"".join(rng.getrandbits(255).to_bytes(32, "little") for _ in range(8)))
@@ -321,6 +349,8 @@ def test_field_op_counts(ops):
     """Field multiplications / squarings executed per operation — the figures the integer-multiply
     roofline in bench.py and DESIGN.md §4 is computed from (reference counts: SURVEY.md §8d)."""
     import bench
+    if ops.device_paths:
+        pytest.skip("the operation counters are host-path instrumentation")
 
     def counts():
         m, s = ctypes.c_ulong(), ctypes.c_ulong()
@@ -343,3 +373,29 @@ def test_field_op_counts(ops):
     assert counts() == bench.OURS_FM_SINGLE["x25519"]
     for op, (m, s) in bench.OURS_FM_SINGLE.items():    # never more field operations than the reference spends
         assert m + s <= bench.REF_FM[op][0] + bench.REF_FM[op][1]
+
+
+def test_device_path_emulation_detects_a_wrong_carry_chain(tmp_path):
+    """Negative control of the "device" flavour: one operand number changed in one carry chain of the rewritten fe.cuh (the
+    second product of a multiplication row accumulates into the wrong word) and the multiplication check fails — the PTX
+    interpreter really executes the device code's chains."""
+    gen = tmp_path / "gen"
+    (gen / "tests" / "host_sim").mkdir(parents=True)
+    subprocess.run([sys.executable, os.path.join(HS, "ptx_rewrite.py"), os.path.join(ROOT, "libeddsa_b200", "csrc"),
+                    str(gen / "libeddsa_b200" / "csrc")], check=True, stdout=subprocess.DEVNULL)
+    f = gen / "libeddsa_b200" / "csrc" / "fe.cuh"
+    text = f.read_text()
+    good = "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %3;"
+    assert text.count(good) == 1                                 # cmad<4>: the row of four products with a carry-out word
+    f.write_text(text.replace(good, "madc.lo.cc.u32 %2, %10, %13, %2; madc.hi.cc.u32 %3, %10, %13, %2;"))
+    (gen / "tests" / "host_sim" / "fe_host.cpp").write_text(open(os.path.join(HS, "fe_host.cpp")).read())
+    so = tmp_path / "libfe_bad.so"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-D__CUDA_ARCH__=1000", "-D__CUDACC__",
+                    "-include", os.path.join(HS, "ptx_emul.h"), "-o", str(so), str(gen / "tests" / "host_sim" / "fe_host.cpp")], check=True)
+    bad = ctypes.CDLL(str(so))
+    rng = random.Random(12)
+    wrong = 0
+    for _ in range(50):
+        a, b = rng.getrandbits(256), rng.getrandbits(256)
+        wrong += val(call(bad.h_fe_mul, W8(a), W8(b))) % P != a * b % P
+    assert wrong > 40
