@@ -19,19 +19,46 @@ HS = os.path.join(HERE, "host_sim")
 HOST_C = os.path.join(os.path.dirname(HERE), "libeddsa_b200", "csrc", "host.c")
 
 
-@pytest.fixture(scope="module")
-def simlib():
-    subprocess.run(["make", "-s", "-C", HS], check=True)
-    return os.path.join(HS, "libeddsa_sim.so")
+_PREFETCHED = {}       # (scenario, env items, args) -> future: the scenario runs of this module, started three at a time in the background
 
 
-def run_scenario(name, env=None, args=(), so=None, timeout=600):
+def _key(name, env, args):
+    return (name, tuple(sorted((env or {}).items())), tuple(args))
+
+
+def _run(name, env=None, args=(), so=None, timeout=600):
     e = {k: v for k, v in os.environ.items() if not k.startswith(("CUDASIM_", "EDDSA_B200_"))}
     e.update(env or {})
     if so:
         e["CUDASIM_SO"] = so
     return subprocess.run([sys.executable, os.path.join(HS, "sim_scenarios.py"), name, *args], env=e, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, text=True, timeout=timeout)
+
+
+def run_scenario(name, env=None, args=(), so=None, timeout=600):
+    fut = _PREFETCHED.pop(_key(name, env, args), None) if so is None else None
+    return fut.result() if fut else _run(name, env, args, so, timeout)
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    """Builds the simulator library and starts every scenario run of this module in the background (each is its own
+    process; three at a time), so that the tests mostly collect results."""
+    import concurrent.futures
+    subprocess.run(["make", "-s", "-C", HS], check=True)
+    pool = concurrent.futures.ThreadPoolExecutor(max_workers=3)
+    for name, env, args in _planned_runs():
+        _PREFETCHED[_key(name, env, args)] = pool.submit(_run, name, env, args)
+    import tempfile
+    scratch = tempfile.mkdtemp(prefix="eddsa_mutants_")
+    for index in range(len(MUTANTS)):
+        _PREFETCHED[("mutant", index)] = pool.submit(_mutant_job, index, os.path.join(scratch, str(index)))
+    yield os.path.join(HS, "libeddsa_sim.so")
+    for fut in _PREFETCHED.values():
+        fut.cancel()
+    pool.shutdown(wait=True)
+    import shutil
+    shutil.rmtree(scratch, ignore_errors=True)
 
 
 SCENARIOS = {
@@ -50,6 +77,30 @@ SCENARIOS = {
 }
 
 
+OTHER_SCHEDULES = [(n, sch) for n in ("chunks", "budget", "multi", "threads", "dev_api", "failures") for sch in ("others-first", "eager", "random")
+                   if n != "failures" or sch == "others-first"]        # the failure sweep: the two adversarial schedules only (12 s each)
+WALKS = [(1, "lazy", 3), (2, "others-first", 4), (3, "random", 2), (6, "lazy", 3)]
+
+
+def _walk_env(seed, schedule, devices):
+    env = {"CUDASIM_DEVICES": str(devices), "CUDASIM_SMS": "1", "CUDASIM_RESIDENT": "32", "CUDASIM_SCHEDULE": schedule}
+    if seed % 3 == 0:
+        env["EDDSA_B200_CHUNK_MB"] = "1"
+    return env
+
+
+def _planned_runs():
+    """In the order the tests below ask for them."""
+    for name in SCENARIOS:
+        yield name, SCENARIOS[name], ()
+    for name, schedule in OTHER_SCHEDULES:
+        yield name, dict(SCENARIOS[name], CUDASIM_SCHEDULE=schedule), ()
+    for seed, schedule, devices in WALKS:
+        yield "fuzz", _walk_env(seed, schedule, devices), (str(seed), "60")
+    yield "scrub", dict(SCENARIOS["scrub"], EDDSA_B200_DEBUG_NO_SCRUB="1"), ()
+    yield "no_device", SCENARIOS["no_device"], ("abort",)
+
+
 @pytest.mark.parametrize("name", list(SCENARIOS))
 def test_host_layer_on_the_simulator(simlib, name):
     """Lazy streams: an operation runs only when something waits for it — the most adversarial legal schedule."""
@@ -57,11 +108,8 @@ def test_host_layer_on_the_simulator(simlib, name):
     assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
 
 
-@pytest.mark.parametrize("schedule", ["others-first", "eager", "random"])
-@pytest.mark.parametrize("name", ["chunks", "budget", "multi", "threads", "dev_api", "failures"])
+@pytest.mark.parametrize("name,schedule", OTHER_SCHEDULES)
 def test_host_layer_under_other_schedules(simlib, name, schedule):
-    if name == "failures" and schedule != "others-first":
-        pytest.skip("the failure sweep runs under the two adversarial schedules only (12 s each)")
     """The same scenarios with every other stream running as far as it can before the awaited one advances (work without a
     dependency runs EARLY — the complement of the lazy schedule), with everything executing at once, and with a random
     interleaving of the streams."""
@@ -69,14 +117,11 @@ def test_host_layer_under_other_schedules(simlib, name, schedule):
     assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
 
 
-@pytest.mark.parametrize("seed,schedule,devices", [(1, "lazy", 3), (2, "others-first", 4), (3, "random", 2), (6, "lazy", 3)])
+@pytest.mark.parametrize("seed,schedule,devices", WALKS)
 def test_random_walk_over_the_c_abi(simlib, seed, schedule, devices):
     """Random operations, sizes, layouts, page-locked / ordinary buffers, device counts, shutdowns and injected failures
     (tools/host_fuzz_campaign.sh runs the long version: 240 runs x 100 steps, profiles/r02_notes.md)."""
-    env = {"CUDASIM_DEVICES": str(devices), "CUDASIM_SMS": "1", "CUDASIM_RESIDENT": "32", "CUDASIM_SCHEDULE": schedule}
-    if seed % 3 == 0:
-        env["EDDSA_B200_CHUNK_MB"] = "1"
-    res = run_scenario("fuzz", env, args=(str(seed), "60"))
+    res = run_scenario("fuzz", _walk_env(seed, schedule, devices), args=(str(seed), "60"))
     assert res.returncode == 0 and "OK fuzz" in res.stdout, res.stdout[-3000:]
 
 
@@ -144,17 +189,28 @@ MUTANTS = [
 ]
 
 
-@pytest.mark.parametrize("what,old,new,scenario", MUTANTS, ids=[m[0] for m in MUTANTS])
-def test_simulator_catches_host_layer_mutants(simlib, tmp_path, what, old, new, scenario):
+def _mutant_job(index, workdir):
+    """Builds host.c with one change and runs the covering scenario under the two adversarial schedules; returns None when a
+    run failed (the mutant was caught), else a description."""
+    what, old, new, scenario = MUTANTS[index]
     src = open(HOST_C).read()
-    assert src.count(old) == 1, f"host.c changed: the text of mutant '{what}' must occur exactly once"
-    mutant_c, so = tmp_path / "host.c", tmp_path / "libeddsa_sim_mutant.so"
-    mutant_c.write_text(src.replace(old, new))
+    if src.count(old) != 1:
+        return f"host.c changed: the text of mutant '{what}' must occur exactly once"
+    os.makedirs(workdir, exist_ok=True)
+    mutant_c, obj, so = os.path.join(workdir, "host.c"), os.path.join(workdir, "host.o"), os.path.join(workdir, "libeddsa_sim_mutant.so")
+    with open(mutant_c, "w") as f:
+        f.write(src.replace(old, new))
     inc = ["-I" + os.path.join(os.path.dirname(HERE), "include"), "-I" + os.path.join(os.path.dirname(HOST_C)), "-I/usr/local/cuda/include"]
-    subprocess.run(["gcc", "-O2", "-std=gnu11", "-fPIC", "-fvisibility=hidden", "-DEDDSA_BUILD", *inc, "-c", str(mutant_c), "-o", str(tmp_path / "host.o")], check=True)
-    subprocess.run(["g++", "-shared", "-o", str(so), os.path.join(HS, "cudasim.o"), str(tmp_path / "host.o"), "-lpthread"], check=True)
+    subprocess.run(["gcc", "-O2", "-std=gnu11", "-fPIC", "-fvisibility=hidden", "-DEDDSA_BUILD", *inc, "-c", mutant_c, "-o", obj], check=True)
+    subprocess.run(["g++", "-shared", "-o", so, os.path.join(HS, "cudasim.o"), obj, "-lpthread"], check=True)
     for schedule in ("lazy", "others-first"):
-        res = run_scenario(scenario, dict(SCENARIOS[scenario], CUDASIM_SCHEDULE=schedule), so=str(so))
-        if res.returncode != 0:
-            return
-    raise AssertionError(f"the '{scenario}' scenario did not notice that {what}")
+        if _run(scenario, dict(SCENARIOS[scenario], CUDASIM_SCHEDULE=schedule), so=so).returncode != 0:
+            return None
+    return f"the '{scenario}' scenario did not notice that {what}"
+
+
+@pytest.mark.parametrize("index", range(len(MUTANTS)), ids=[m[0] for m in MUTANTS])
+def test_simulator_catches_host_layer_mutants(simlib, tmp_path, index):
+    fut = _PREFETCHED.pop(("mutant", index), None)
+    verdict = fut.result() if fut else _mutant_job(index, str(tmp_path))
+    assert verdict is None, verdict
