@@ -741,7 +741,7 @@ def scenario_fuzz():
         return out
 
     for step in range(steps):
-        what = r.choice(["fe_add", "fe_add", "sk_conv", "sk_conv", "verify", "verify", "sign", "x25519_base", "shutdown", "devices"])
+        what = r.choice(["fe_add", "fe_add", "sk_conv", "sk_conv", "verify", "verify", "sign", "x25519_base", "shutdown", "devices", "dev_api"])
         if what == "shutdown":
             ed.shutdown()
             assert sim.live()[0] == lost_blocks, (step, sim.live(), lost_blocks)
@@ -751,6 +751,44 @@ def scenario_fuzz():
             continue
         caller_dev = int(r.integers(0, ndev))
         L.cudasim_set_device(caller_dev)
+        if what == "dev_api":
+            # the device-pointer entry points on the caller's current device and a stream of its own: verify + genpub
+            n = int(r.choice([1, 33, 200]))
+            lo = int(r.integers(0, 700 - n + 1))
+            off = np.ascontiguousarray(poff[lo:lo + n + 1], np.uint64)
+            bad_sig, bad_pub = mutate(r, psig[lo:lo + n], ppub[lo:lo + n], 0.25)
+            want = cpu.verify(bad_sig, bad_pub, pmsgs, off, 0)
+            devs = []
+
+            def dev(arr, pad=16):
+                arr = np.ascontiguousarray(arr)
+                a, p = sim.user_array(arr.nbytes + pad, K_DEVICE, caller_dev)
+                a[:arr.nbytes] = arr.view(np.uint8).reshape(-1)
+                devs.append(p)
+                return a, p
+
+            d_sig, d_pub, d_msgs, d_off, d_sec = dev(bad_sig), dev(bad_pub), dev(pmsgs), dev(off), dev(psec[lo:lo + n])
+            d_ok, d_out = dev(np.zeros(n, np.uint8), 0), dev(np.zeros((n, 32), np.uint8), 0)
+            st = L.cudasim_stream_create(caller_dev)
+            fail_api, fail_nth = (int(r.choice([API_POOL_ALLOC, API_LAUNCH, API_MALLOC])), int(r.integers(1, 3))) if r.random() < 0.3 else (-1, 0)
+            if fail_api >= 0:
+                L.cudasim_fail(fail_api, fail_nth)
+            rc1 = L.ed25519_verify_batch_dev(n, d_ok[1], d_sig[1], d_pub[1], d_msgs[1], d_off[1], 0, st)
+            rc2 = L.ed25519_genpub_batch_dev(n, d_out[1], d_sec[1], st)
+            L.cudasim_clear_faults()
+            L.cudasim_sync_all()
+            where = f"seed {seed} step {step}: dev_api n={n} fail={fail_api, fail_nth} rc={rc1, rc2}"
+            assert fail_api >= 0 or (rc1, rc2) == (0, 0), where
+            if rc1 == 0:
+                eq(d_ok[0][:n], want, where + " verify_batch_dev")
+            if rc2 == 0:
+                eq(d_out[0][:32 * n].reshape(-1, 32), ppub[lo:lo + n], where + " genpub_batch_dev")
+            assert sim.pending() == 0 and sim.errors() == 0, where + " " + sim.first_error()
+            assert L.cudasim_current_device() == caller_dev, where
+            for p_ in devs:
+                L.cudasim_user_free(p_)
+            log.append((step, what, n, [], fail_api, fail_nth))
+            continue
         fail_api, fail_nth = (int(r.integers(0, 16)), int(r.integers(1, 25))) if r.random() < 0.3 else (-1, 0)
         if fail_api == API_SET_DEVICE:
             fail_nth = 1            # a later cudaSetDevice is the one that RESTORES the caller's device: nothing could be done about that

@@ -120,7 +120,7 @@ def test_host_layer_under_other_schedules(simlib, name, schedule):
 @pytest.mark.parametrize("seed,schedule,devices", WALKS)
 def test_random_walk_over_the_c_abi(simlib, seed, schedule, devices):
     """Random operations, sizes, layouts, page-locked / ordinary buffers, device counts, shutdowns and injected failures
-    (tools/host_fuzz_campaign.sh runs the long version: 240 runs x 100 steps, profiles/r02_notes.md)."""
+    (tools/host_fuzz_campaign.sh runs the long version: 400 runs x 100 steps, profiles/r02_notes.md)."""
     res = run_scenario("fuzz", _walk_env(seed, schedule, devices), args=(str(seed), "60"))
     assert res.returncode == 0 and "OK fuzz" in res.stdout, res.stdout[-3000:]
 
