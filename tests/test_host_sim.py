@@ -399,3 +399,42 @@ def test_device_path_emulation_detects_a_wrong_carry_chain(tmp_path):
         a, b = rng.getrandbits(256), rng.getrandbits(256)
         wrong += val(call(bad.h_fe_mul, W8(a), W8(b))) % P != a * b % P
     assert wrong > 40
+
+
+def test_ragged_tile_ordering():
+    """kernel_common.cuh: the message kernels visit a tile of consecutive operations of a ragged batch in order of message length
+    (ragged_key + the shared-memory bitonic sort block_sort_u32).  The device code, compiled for the host as a block of one
+    thread: every operation of the tile is visited exactly once, in non-decreasing (capped) length order; operations past the
+    end of the batch sort last; huge lengths saturate instead of overflowing into the index bits."""
+    gen = os.path.join(HS, "_ptx")
+    os.makedirs(os.path.join(gen, "tests", "host_sim"), exist_ok=True)
+    subprocess.run([sys.executable, os.path.join(HS, "ptx_rewrite.py"), os.path.join(ROOT, "libeddsa_b200", "csrc"),
+                    os.path.join(gen, "libeddsa_b200", "csrc")], check=True, stdout=subprocess.DEVNULL)
+    gsrc = os.path.join(gen, "tests", "host_sim", "kernel_common_host.cpp")
+    with open(gsrc, "w") as f:
+        f.write(open(os.path.join(HS, "kernel_common_host.cpp")).read())
+    so = os.path.join(HS, "libkernel_common_host_ptx.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-D__CUDA_ARCH__=1000", "-D__CUDACC__",
+                    "-I" + os.path.join(HS, "fake_cuda"), "-include", os.path.join(HS, "ptx_emul.h"), "-o", so, gsrc], check=True)
+    lib = ctypes.CDLL(so)
+    lib.hs_tile_order.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_int]
+    rng = np.random.default_rng(13)
+    for bits in (9, 10, 11):
+        tile = 1 << bits
+        cap = (1 << (32 - bits)) - 2
+        for n, base, maxlen in ((tile, 0, 300), (3 * tile + 17, 3 * tile, 5000), (tile + 5, 0, 1), (2 * tile, tile, 0), (tile // 2, 0, 70)):
+            lens = rng.integers(0, maxlen + 1, size=n).astype(np.uint64)
+            if maxlen == 5000:
+                lens[base + 3] = cap + 12345                      # longer than the key can say
+                lens[base + 4] = 1 << 40
+            off = np.zeros(n + 1, np.uint64)
+            off[1:] = np.cumsum(lens)
+            keys = np.zeros(tile, np.uint32)
+            lib.hs_tile_order(keys.ctypes.data, off.ctypes.data, base, n, bits)
+            live = min(tile, n - base)
+            assert (np.diff(keys.astype(np.int64)) >= 0).all()
+            idx = (keys[:live] & (tile - 1)).astype(np.int64)
+            assert sorted(idx.tolist()) == list(range(live))         # every operation of the tile exactly once
+            assert (keys[live:] == 0xFFFFFFFF).all()                 # slots past the end of the batch sort last
+            want = np.minimum(lens[base + idx], cap).astype(np.int64)
+            assert ((keys[:live] >> bits).astype(np.int64) == want).all() and (np.diff(want) >= 0).all()
