@@ -79,6 +79,7 @@ std::vector<Launch> g_launch_log;
 long g_fail_countdown[API_COUNT];
 int g_fault[MAX_DEV];
 int g_waves = 16, g_full_scalars = 0;
+bool g_keep_freed = false;
 int g_resident = 4 * 128;          // resident threads per SM of the verify loop kernel; CUDASIM_RESIDENT: smaller waves make the
                                    // verify chunk schedule cheap to exercise
 
@@ -99,6 +100,7 @@ void configure() {
     if (getenv("CUDASIM_SMS")) g_sms = atoi(getenv("CUDASIM_SMS"));
     if (getenv("CUDASIM_THREADS")) g_threads = atoi(getenv("CUDASIM_THREADS"));
     if (getenv("CUDASIM_RESIDENT")) g_resident = atoi(getenv("CUDASIM_RESIDENT"));
+    if (getenv("CUDASIM_KEEP_FREED")) g_keep_freed = atoi(getenv("CUDASIM_KEEP_FREED")) != 0;
     if (g_ndev > MAX_DEV) g_ndev = MAX_DEV;
     if (g_sms < 1) g_sms = 1;
     if (g_threads < 1) g_threads = 1;
@@ -227,7 +229,9 @@ void exec_front(Stream *s) {
         if (op.ev->done_ticket < op.ticket) sim_error("stream wait on an event whose record can never complete");
         break;
     case Op::FREE:
-        sim_free(op.dst, K_DEVICE);
+        // CUDASIM_KEEP_FREED=1: a block returned to the pool keeps its contents and stays visible to cudasim_find, as pool memory
+        // does on the device — what a kernel left in its scratch can then be searched for secrets
+        if (!g_keep_freed) sim_free(op.dst, K_DEVICE);
         break;
     }
 }
@@ -257,6 +261,7 @@ void parallel_for(size_t n, const std::function<void(size_t)> &body) {
     for (auto &x : th) x.join();
 }
 
+#if !defined(CUDASIM_REAL_KERNELS)   // (the flavour with the REAL kernels links the rewritten kernels_*.cu instead: simt_emul.h)
 // ---- the tables the kernels read, built exactly as the device builds them (k_wtab_base / k_wtab_build, k_comb_*) ----
 const u32 *host_comb() {
     static u32 *tab = nullptr;
@@ -323,8 +328,10 @@ bool need_msgs(const uint8_t *msgs, const unsigned long long *off, unsigned long
     return need_dev(msgs, n * fixed_len, dev, what);
 }
 
+#endif
 }  // namespace
 
+#if !defined(CUDASIM_REAL_KERNELS)
 // =====================================================================================================================
 // launchers (edg_internal.h)
 // =====================================================================================================================
@@ -511,6 +518,22 @@ int edg_launch_sc_selftest(size_t n, uint8_t *out, const uint8_t *a, const uint8
         });
     });
 }
+
+#else
+extern "C" {
+// the REAL kernels (tests/host_sim/simt_emul.h): a launch arrives as a closure that runs the whole grid
+int cudasim_enqueue_kernel(void *stream, void (*fn)(void *), void *arg) {
+    std::lock_guard<std::recursive_mutex> lk(G);
+    configure();
+    Stream *s = stream_of((cudaStream_t)stream);
+    if (g_fault[s->dev] || inject(API_LAUNCH)) { t_last = g_fault[s->dev] ? (cudaError_t)g_fault[s->dev] : cudaErrorLaunchFailure; return (int)t_last; }
+    Op op;
+    op.type = Op::KERNEL;
+    op.fn = [fn, arg] { fn(arg); };
+    enqueue(s, std::move(op));
+    return 0;
+}
+#endif
 
 // =====================================================================================================================
 // CUDA runtime API (the subset host.c uses)

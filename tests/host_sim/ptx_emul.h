@@ -28,12 +28,17 @@ struct uint4 { uint32_t x, y, z, w; };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { uint4 v = {x, y, z, w}; return v; }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 
+#if !defined(EDG_SIMT)
 // one lane of a one-thread block
 struct edg_dim3 { unsigned x, y, z; };
 static const edg_dim3 blockDim = {1, 1, 1}, gridDim = {1, 1, 1}, threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0};
 static inline unsigned __shfl_sync(unsigned, unsigned v, int, int = 32) { return v; }
 static inline int __reduce_max_sync(unsigned, int v) { return v; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
+#else
+// many lanes: tests/host_sim/simt_emul.h supplies the thread geometry and the warp collectives
+namespace edg_ptx { inline void mma_u8(int k, uint64_t *reg, const uint64_t *idx); }
+#endif
 
 // CUDA integer intrinsics (CUDA math API semantics)
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t shift) {
@@ -69,9 +74,9 @@ template <typename T> static inline Arg in(const T &x, const char *c) {
 }
 template <typename T> static inline Arg in(T *const &x, const char *) { Arg a = {nullptr, (uint64_t)(uintptr_t)x, 8}; return a; }
 
-enum Op { ADD, ADDC, SUB, SUBC, MAD_LO, MADC_LO, MADC_HI, MAD_HI, CP_ASYNC, NOP };
+enum Op { ADD, ADDC, SUB, SUBC, MAD_LO, MADC_LO, MADC_HI, MAD_HI, CP_ASYNC, NOP, MMA_K16, MMA_K32 };
 struct Operand { bool imm; uint64_t v; };            // register index or immediate
-struct Ins { Op op; bool cc; int nops; Operand o[4]; };
+struct Ins { Op op; bool cc; int nops; Operand o[16]; };
 struct Prog { std::vector<Ins> ins; };
 
 static inline Operand parse_operand(std::string t) {
@@ -112,9 +117,13 @@ static inline Prog compile(const char *tmpl) {
         else if (opc == "madc.hi.u32") { in.op = MADC_HI; }
         else if (opc == "cp.async.cg.shared.global") { in.op = CP_ASYNC; }
         else if (opc == "cp.async.commit_group" || opc == "cp.async.wait_group") { in.op = NOP; rest = ""; }
+        else if (opc == "mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32") { in.op = MMA_K16; }
+        else if (opc == "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32") { in.op = MMA_K32; }
         else { fprintf(stderr, "ptx_emul: instruction '%s' is not modelled\n", opc.c_str()); abort(); }
+        for (char &ch : rest)
+            if (ch == '{' || ch == '}') ch = ' ';           // operand groups of mma: D(4), A(2 | 4), B(1 | 2), C(4), in order
         size_t q = 0;
-        while (q < rest.size() && in.nops < 4) {
+        while (q < rest.size() && in.nops < 16) {
             size_t comma = rest.find(',', q);
             if (comma == std::string::npos) comma = rest.size();
             std::string t = rest.substr(q, comma - q);
@@ -164,6 +173,17 @@ static inline void run(const Prog &p, Arg *a, int n) {
             memcpy(shared_base + ((uint32_t)val(in.o[0]) - kSharedBias), (const void *)(uintptr_t)val(in.o[1]), (size_t)val(in.o[2]));
             break;
         case NOP: break;
+        case MMA_K16: case MMA_K32: {
+#if defined(EDG_SIMT)
+            uint64_t idx[16];
+            for (int k = 0; k < in.nops; k++) idx[k] = in.o[k].imm ? ~0ull : in.o[k].v;
+            mma_u8(in.op == MMA_K16 ? 16 : 32, reg, idx);
+#else
+            fprintf(stderr, "ptx_emul: mma.sync needs the multi-lane build (simt_emul.h)\n");
+            abort();
+#endif
+            break;
+        }
         }
     }
     for (int i = 0; i < n; i++)

@@ -3,7 +3,8 @@ code paths (everything under `#if defined(__CUDA_ARCH__)`: the carry-chain field
 helpers of hgcd.cuh, the funnel-shift SHA-512, 128-bit loads, cp.async staging) can be compiled for the host and checked
 on the CPU by the same unit tests as the portable host paths (tests/test_host_sim.py).
 
-    python ptx_rewrite.py <src dir> <dst dir>      # every *.cuh / *.h of src, asm statements replaced, written to dst
+    python ptx_rewrite.py <src dir> <dst dir>      # every *.cuh / *.h / *.cu of src, asm statements (and, in the .cu files,
+                                                   # kernel launches: see rewrite_launches) replaced, written to dst
 
 Every statement
 
@@ -126,16 +127,49 @@ def rewrite(text, name):
     return "".join(out), count
 
 
+LAUNCH_RE = re.compile(r"([A-Za-z_][A-Za-z_0-9]*(?:<[^<>;(){}]*>)?)\s*<<<")
+DYN_SMEM_RE = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(\w+)\s+(\w+)\[\];")
+
+
+def rewrite_launches(text):
+    """kernel<<<grid, block[, smem[, stream]]>>>(args);  ->  edg_simt::launch(grid, block, smem, stream, [=] { kernel(args); });
+    and  extern __shared__ T name[];  ->  T *name = (T *)the block's dynamic shared memory  (simt_emul.h)."""
+    out, pos, count = [], 0, 0
+    while True:
+        m = LAUNCH_RE.search(text, pos)
+        if not m:
+            break
+        close = text.index(">>>", m.end())
+        cfg = [c.strip() for c in split_top(text[m.end():close], ",")]
+        while len(cfg) < 4:
+            cfg.append("0")
+        args_open = text.index("(", close)
+        args_close = find_matching_paren(text, args_open)
+        semi = text.index(";", args_close)
+        out.append(text[pos:m.start()])
+        out.append(f"edg_simt::launch({cfg[0]}, {cfg[1]}, {cfg[2]}, (void *)({cfg[3]}), [=] {{ {m.group(1)}{text[args_open:args_close + 1]}; }});")
+        pos = semi + 1
+        count += 1
+    out.append(text[pos:])
+    text = "".join(out)
+    text = DYN_SMEM_RE.sub(lambda d: f"{d.group(1)} *{d.group(2)} = ({d.group(1)} *)edg_simt::cur->blk->dyn;", text)
+    return text, count
+
+
 def main(src, dst):
     os.makedirs(dst, exist_ok=True)
     total = 0
+    launches = 0
     for f in sorted(os.listdir(src)):
-        if f.endswith((".cuh", ".h")):
+        if f.endswith((".cuh", ".h", ".cu")):
             new, n = rewrite(open(os.path.join(src, f)).read(), f)
             total += n
-            with open(os.path.join(dst, f), "w") as fh:
+            if f.endswith(".cu"):
+                new, k = rewrite_launches(new)
+                launches += k
+            with open(os.path.join(dst, f + ".cpp" if f.endswith(".cu") else f), "w") as fh:
                 fh.write("// GENERATED by tests/host_sim/ptx_rewrite.py from libeddsa_b200/csrc/" + f + " — test infrastructure, do not edit\n" + new)
-    print(f"rewrote {total} asm statements")
+    print(f"rewrote {total} asm statements and {launches} kernel launches")
 
 
 if __name__ == "__main__":

@@ -878,6 +878,100 @@ def scenario_fuzz():
     print("steps:", len(log), "failures injected:", sum(1 for x in log if x[4] >= 0))
 
 
+def scenario_real_kernels():
+    """The REAL kernels and launchers (libeddsa_b200/csrc/kernels_*.cu, rewritten for the SIMT emulator of simt_emul.h: OS threads
+    as lanes, rendezvous for __syncthreads / warp collectives / mma.sync, the PTX interpreter for the carry chains) behind the real
+    host layer, on the reference's own vectors and the committed fixtures: passes, tiles sorted by message length, the verify
+    permutation, the comb kernel with its tensor-core table lookup, shared inversions — all of it as shipped, without a GPU."""
+    import golden_util as gu
+    from cpu_ref import best_cpu_impl
+    assert "sim_kernels" in SIM_SO and os.environ.get("EDDSA_B200_VERIFY_WAVES") == "1"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed = sim.ed
+    r = rng(21)
+    # the reference's x25519 table (1024 rows, 508 of them with bit 255 set) and the edge cases: k_x25519, shared inversions of 32
+    point, scalar, result = gu.x25519_kat()
+    eq(ed.x25519_batch(scalar, point), result, "x25519 KAT table")
+    point, scalar, result = gu.x25519_edge()
+    eq(ed.x25519_batch(scalar, point), result, "x25519 edge cases")
+    bs, bo = gu.x25519_base_kat()
+    eq(ed.x25519_base_batch(bs), bo, "x25519_base fixture")                  # k_comb<1>
+    # Ed25519 KAT: 1024 rows, message length = row index (a ragged batch: two tiles of 512 sorted by length)
+    sec, pub, sig, msgs = gu.ed25519_kat()
+    blob, off = gu.ragged(msgs)
+    eq(ed.ed25519_genpub_batch(sec), pub, "genpub KAT")                      # k_expand_key + k_comb<0>
+    eq(ed.ed25519_sign_batch(sec, pub, blob, off, 0), sig, "sign KAT")       # k_sign_nonce<1> + k_comb<0> + k_sign_finish<1>
+    assert ed.ed25519_verify_batch(sig, pub, blob, off, 0).all()             # k_verify_scalars<1> + k_verify_points + k_verify
+    sim.clean()
+    # every adversarial row (22 classes incl. torsion): 2960 decisions, three passes of 1024 signatures
+    asig, apub, amsgs, cls, expect = gu.verify_adv()
+    ablob, aoff = gu.ragged(amsgs)
+    got = ed.ed25519_verify_batch(asig, apub, ablob, aoff, 0)
+    bad = [(i, int(cls[i])) for i in range(len(got)) if got[i] != expect[i]]
+    assert not bad, bad[:10]
+    # fixed-length messages (the non-ragged kernels), wrong-pub signing, key conversions
+    wsec, wpub, wsig, wmsgs = gu.sign_wrongpub()
+    eq(ed.ed25519_sign_batch(wsec, wpub, np.frombuffer(b"".join(wmsgs), np.uint8), None, 64), wsig, "sign with the caller's (wrong) pub")
+    n = 1100
+    fsec, fpub, fmsgs, _, fsig = make_signed(cpu, r, n, fixed_len=64)
+    eq(ed.ed25519_sign_batch(fsec, fpub, fmsgs, None, 64), fsig, "sign, fixed 64-byte messages")
+    bsig, bpub = mutate(r, fsig, fpub, 0.1)
+    eq(ed.ed25519_verify_batch(bsig, bpub, fmsgs, None, 64), cpu.verify(bsig, bpub, fmsgs, None, 64), "verify, fixed 64-byte messages")
+    edsk, edpk, xsk, xpk = gu.convert_kat()
+    eq(ed.sk_ed25519_to_x25519_batch(edsk), xsk, "sk conversion")
+    eq(ed.pk_ed25519_to_x25519_batch(edpk), xpk, "pk conversion")
+    sim.clean()
+    # the tables the device builds (k_wtab_base / k_wtab_build, k_comb_base / k_comb_rows / k_comb_layout)
+    import edmodel as em
+    em.check_comb_table(ed.comb_table(), 6)
+    assert ed.launch_count() >= 30
+    ed.shutdown()
+    assert sim.live() == (0, 0)
+
+
+def scenario_kernel_scrub():
+    """The kernels wipe their own scratch: the secret scalar a = clamp(SHA512(sk)[0..31]) mod L that k_expand_key / k_sign_nonce hand
+    to the comb, and the nonce r of a signature, are gone from the pool block when the call returns (CUDASIM_KEEP_FREED=1 keeps
+    returned pool blocks searchable, as pool memory keeps its contents on the device).  With the wipes compiled out (argv[2] ==
+    "expect-residue": a mutant of the kernel source built by the test) the same search finds them."""
+    import hashlib
+    from cpu_ref import best_cpu_impl
+    from edmodel import L as ORDER
+    assert "sim_kernels" in SIM_SO and os.environ.get("CUDASIM_KEEP_FREED") == "1"
+    expect_residue = len(sys.argv) > 2 and sys.argv[2] == "expect-residue"
+    sim, cpu = Sim(), best_cpu_impl()
+    ed = sim.ed
+    r = rng(22)
+    n = 300
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, fixed_len=48)
+
+    def secret_scalar(sk):
+        h = bytearray(hashlib.sha512(bytes(sk)).digest())
+        h[0] &= 248
+        h[31] = (h[31] & 127) | 64
+        a = int.from_bytes(bytes(h[:32]), "little") % ORDER
+        nonce_prefix = bytes(h[32:])
+        return a, nonce_prefix
+
+    scalars, nonces = [], []
+    for i in range(n):
+        a, prefix = secret_scalar(sec[i])
+        scalars.append(np.frombuffer(a.to_bytes(32, "little"), np.uint8))
+        rr = int.from_bytes(hashlib.sha512(prefix + bytes(msgs[48 * i:48 * i + 48])).digest(), "little") % ORDER
+        nonces.append(np.frombuffer(rr.to_bytes(32, "little"), np.uint8))
+    eq(ed.ed25519_genpub_batch(sec), pub, "genpub")
+    left_genpub = sim.find(scalars)
+    eq(ed.ed25519_sign_batch(sec, pub, msgs, None, 48), sig, "sign")
+    left_sign = sim.find(scalars) + sim.find(nonces)
+    left_keys = sim.find([sec[i] for i in range(n)])
+    print("residue: genpub", left_genpub, "sign", left_sign, "keys", left_keys)
+    assert left_keys == 0
+    if expect_residue:
+        assert left_genpub >= n and left_sign >= 2 * n
+    else:
+        assert left_genpub == 0 and left_sign == 0
+
+
 def scenario_no_device():
     """No usable device: the batch calls report it (there is no CPU path to fall back to)."""
     assert os.environ.get("CUDASIM_DEVICES") == "0"
