@@ -972,6 +972,25 @@ def scenario_kernel_scrub():
         assert left_genpub == 0 and left_sign == 0
 
 
+def scenario_tsan_workload():
+    """The workload of tools/host_tsan.sh (the real kernels under ThreadSanitizer): ragged sign / verify (tile sort in shared memory,
+    permutation counters, staging of the verify loop), genpub (comb table staging, exchange areas, mma rendezvous), x25519."""
+    from cpu_ref import best_cpu_impl
+    sim, cpu = Sim(), best_cpu_impl()
+    ed = sim.ed
+    r = rng(3)
+    n = 700
+    sec, pub, msgs, off, sig = make_signed(cpu, r, n, max_len=90)
+    eq(ed.ed25519_genpub_batch(sec), pub, "genpub")
+    eq(ed.ed25519_sign_batch(sec, pub, msgs, off, 0), sig, "sign")
+    bs, bp = mutate(r, sig, pub, 0.2)
+    eq(ed.ed25519_verify_batch(bs, bp, msgs, off, 0), cpu.verify(bs, bp, msgs, off, 0), "verify")
+    pts = rand_rows(r, 200)
+    eq(ed.x25519_batch(sec[:200], pts), cpu.x25519(sec[:200], pts), "x25519")
+    eq(ed.x25519_base_batch(sec[:200]), cpu.x25519_base(sec[:200]), "x25519_base")
+    assert sim.errors() == 0
+
+
 def scenario_no_device():
     """No usable device: the batch calls report it (there is no CPU path to fall back to)."""
     assert os.environ.get("CUDASIM_DEVICES") == "0"

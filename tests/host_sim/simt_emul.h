@@ -45,7 +45,7 @@ struct Rendezvous {                                   // a reusable barrier whos
         if (live > 0 && arrived >= live) { arrived = 0; gen++; cv.notify_all(); }
     }
 };
-struct Warp : Rendezvous { uint32_t slot[32][8]; };
+struct Warp : Rendezvous { uint32_t slot[32][8]; int lanes = 0; };     // lanes: the warp's width (live shrinks as lanes return)
 struct Block : Rendezvous { std::vector<Warp> warps; char *dyn = nullptr; };
 struct Lane { dim3 tid, bid, bdim, gdim; Block *blk; Warp *warp; unsigned lane; };
 inline thread_local Lane *cur = nullptr;
@@ -68,7 +68,7 @@ inline void run_grid(dim3 grid, dim3 block, size_t smem, const std::function<voi
                 Block blk;
                 blk.live = (int)nthreads;
                 blk.warps = std::vector<Warp>(nwarps);
-                for (unsigned w = 0; w < nwarps; w++) blk.warps[w].live = (int)(w + 1 < nwarps ? 32 : nthreads - 32 * w);
+                for (unsigned w = 0; w < nwarps; w++) blk.warps[w].live = blk.warps[w].lanes = (int)(w + 1 < nwarps ? 32 : nthreads - 32 * w);
                 std::vector<char> dyn(smem + 64, (char)0xA5);
                 blk.dyn = dyn.data() + (64 - ((uintptr_t)dyn.data() & 63)) % 64;
                 std::vector<std::thread> th;
@@ -121,7 +121,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) {
     if (edg_one_lane(mask)) return pred ? mask : 0u;
     uint32_t all[32][8], p = pred ? 1u : 0u, r = 0;
     edg_simt::warp_all(&p, 1, all);
-    for (int l = 0; l < edg_simt::cur->warp->live; l++) r |= all[l][0] << l;
+    for (int l = 0; l < edg_simt::cur->warp->lanes; l++) r |= all[l][0] << l;
     return r & mask;
 }
 static inline int __reduce_max_sync(unsigned mask, int v) {
@@ -129,7 +129,7 @@ static inline int __reduce_max_sync(unsigned mask, int v) {
     uint32_t all[32][8], x = (uint32_t)v;
     edg_simt::warp_all(&x, 1, all);
     int m = v;
-    for (int l = 0; l < edg_simt::cur->warp->live; l++) m = (int)all[l][0] > m ? (int)all[l][0] : m;
+    for (int l = 0; l < edg_simt::cur->warp->lanes; l++) m = (int)all[l][0] > m ? (int)all[l][0] : m;
     return m;
 }
 
