@@ -973,7 +973,7 @@ def scenario_kernel_scrub():
 
 
 def scenario_tsan_workload():
-    """The workload of tools/host_tsan.sh (the real kernels under ThreadSanitizer): ragged sign / verify (tile sort in shared memory,
+    """The workload of tools/host_sanitize.sh (the real kernels under ThreadSanitizer): ragged sign / verify (tile sort in shared memory,
     permutation counters, staging of the verify loop), genpub (comb table staging, exchange areas, mma rendezvous), x25519."""
     from cpu_ref import best_cpu_impl
     sim, cpu = Sim(), best_cpu_impl()
