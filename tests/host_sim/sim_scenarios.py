@@ -917,6 +917,28 @@ def scenario_real_kernels():
     eq(ed.ed25519_sign_batch(fsec, fpub, fmsgs, None, 64), fsig, "sign, fixed 64-byte messages")
     bsig, bpub = mutate(r, fsig, fpub, 0.1)
     eq(ed.ed25519_verify_batch(bsig, bpub, fmsgs, None, 64), cpu.verify(bsig, bpub, fmsgs, None, 64), "verify, fixed 64-byte messages")
+    # message lengths around the SHA-512 block boundaries and long ones, at every byte alignment of the blob (the 128-bit, the
+    # unaligned-block and the byte-wise loaders of sha512.cuh), as one ragged batch
+    lens = [0, 1, 55, 56, 63, 64, 111, 112, 127, 128, 129, 239, 240, 255, 256, 1023, 1025]
+    lens = [l for l in lens for _ in range(2)] + [4096 + 7, 16384]
+    pad = r.integers(0, 16, size=len(lens))                             # gaps between messages: arbitrary alignment
+    eoff = np.zeros(len(lens) + 1, np.uint64)
+    pos = 3
+    starts = []
+    for l, g in zip(lens, pad):
+        starts.append(pos)
+        pos += l + int(g)
+    # offsets must be contiguous for the batch ABI: message i = blob[off[i] .. off[i+1]) — so the gaps become part of the NEXT
+    # message's prefix here; alignment still varies because the lengths do
+    eoff[0] = 3
+    eoff[1:] = 3 + np.cumsum(np.array(lens, np.uint64) + pad.astype(np.uint64))
+    eblob = r.integers(0, 256, size=int(eoff[-1]) + 1, dtype=np.uint8)
+    esec = rand_rows(r, len(lens))
+    epub = cpu.genpub(esec)
+    esig = cpu.sign(esec, epub, eblob, eoff, 0)
+    eq(ed.ed25519_sign_batch(esec, epub, eblob, eoff, 0), esig, "sign, block-boundary lengths at odd alignments")
+    bsig2, bpub2 = mutate(r, esig, epub, 0.2)
+    eq(ed.ed25519_verify_batch(bsig2, bpub2, eblob, eoff, 0), cpu.verify(bsig2, bpub2, eblob, eoff, 0), "verify, block-boundary lengths")
     edsk, edpk, xsk, xpk = gu.convert_kat()
     eq(ed.sk_ed25519_to_x25519_batch(edsk), xsk, "sk conversion")
     eq(ed.pk_ed25519_to_x25519_batch(edpk), xpk, "pk conversion")
@@ -924,7 +946,7 @@ def scenario_real_kernels():
     # the tables the device builds (k_wtab_base / k_wtab_build, k_comb_base / k_comb_rows / k_comb_layout)
     import edmodel as em
     em.check_comb_table(ed.comb_table(), 6)
-    assert ed.launch_count() >= 30
+    assert ed.launch_count() >= 36
     ed.shutdown()
     assert sim.live() == (0, 0)
 
@@ -989,6 +1011,22 @@ def scenario_tsan_workload():
     eq(ed.x25519_batch(sec[:200], pts), cpu.x25519(sec[:200], pts), "x25519")
     eq(ed.x25519_base_batch(sec[:200]), cpu.x25519_base(sec[:200]), "x25519_base")
     assert sim.errors() == 0
+
+
+def scenario_real_kernels_full_scalars():
+    """EDDSA_B200_DEBUG_FULL_SCALARS=1 on the real kernels: every signature takes the full-length fallback (rho, tau) = (1, t) of the
+    half-size-scalar verification — 64 windows instead of 33 — and every adversarial decision stays the same."""
+    import golden_util as gu
+    assert "sim_kernels" in SIM_SO and os.environ.get("EDDSA_B200_DEBUG_FULL_SCALARS") == "1"
+    sim = Sim()
+    ed = sim.ed
+    asig, apub, amsgs, cls, expect = gu.verify_adv()
+    pick = list(range(0, len(asig), 4)) + [i for i in range(len(asig)) if cls[i] >= 16]
+    ablob, aoff = gu.ragged([amsgs[i] for i in pick])
+    got = ed.ed25519_verify_batch(asig[pick], apub[pick], ablob, aoff, 0)
+    bad = [(pick[k], int(cls[pick[k]])) for k in range(len(pick)) if got[k] != expect[pick[k]]]
+    assert not bad, bad[:10]
+    sim.clean()
 
 
 def scenario_no_device():

@@ -83,6 +83,7 @@ SCENARIOS = {
 KERNELS_SO = os.path.join(HS, "libeddsa_sim_kernels.so")
 # (the lifecycle scenario and the other stream schedules pass on it too; left out of the suite for time: 35 s / 23 s each)
 REAL_KERNEL_RUNS = [("real_kernels", {"CUDASIM_DEVICES": "1", "EDDSA_B200_VERIFY_WAVES": "1"}),
+                    ("real_kernels_full_scalars", {"CUDASIM_DEVICES": "1", "EDDSA_B200_DEBUG_FULL_SCALARS": "1"}),
                     ("all_ops", {"CUDASIM_DEVICES": "1"})]
 
 OTHER_SCHEDULES = [(n, sch) for n in ("chunks", "budget", "multi", "threads", "dev_api", "failures") for sch in ("others-first", "eager", "random")
