@@ -81,10 +81,9 @@ SCENARIOS = {
 
 # the REAL kernels and launchers on the SIMT emulator (host_sim/simt_emul.h) behind the same host layer and simulator
 KERNELS_SO = os.path.join(HS, "libeddsa_sim_kernels.so")
-# (the lifecycle scenario and the other stream schedules pass on it too; left out of the suite for time: 35 s / 23 s each)
+# (the all_ops and lifecycle scenarios and the other stream schedules pass on it too; left out of the suite for time: ~30 s each)
 REAL_KERNEL_RUNS = [("real_kernels", {"CUDASIM_DEVICES": "1", "EDDSA_B200_VERIFY_WAVES": "1"}),
-                    ("real_kernels_full_scalars", {"CUDASIM_DEVICES": "1", "EDDSA_B200_DEBUG_FULL_SCALARS": "1"}),
-                    ("all_ops", {"CUDASIM_DEVICES": "1"})]
+                    ("real_kernels_full_scalars", {"CUDASIM_DEVICES": "1", "EDDSA_B200_DEBUG_FULL_SCALARS": "1"})]
 
 OTHER_SCHEDULES = [(n, sch) for n in ("chunks", "budget", "multi", "threads", "dev_api", "failures") for sch in ("others-first", "eager", "random")
                    if n != "failures" or sch == "others-first"]        # the failure sweep: the two adversarial schedules only (12 s each)
@@ -131,7 +130,7 @@ def test_real_kernels_on_the_simt_emulator(simlib, name, env):
     """kernels_*.cu as shipped — kernel launches and inline PTX rewritten (ptx_rewrite.py), lanes as OS threads with real
     rendezvous for __syncthreads, the warp collectives and mma.sync (simt_emul.h) — behind the real host layer: the reference's
     x25519 table, the Ed25519 KAT with ragged messages, all 2 960 adversarial verify decisions, wrong-pub signing, conversions,
-    the device-built tables; plus the all_ops and lifecycle scenarios.  Bit-exact, without a GPU."""
+    the device-built tables, SHA block-boundary lengths at odd alignments, the full-length fallback.  Bit-exact, without a GPU."""
     res = run_scenario(name, env, so=KERNELS_SO)
     assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
 
