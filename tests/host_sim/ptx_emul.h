@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -54,6 +55,9 @@ static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 
 namespace edg_ptx {
+
+// field multiplications / squarings executed (EDG_EMUL_COUNT builds: the real kernels on the SIMT emulator)
+inline std::atomic<unsigned long long> cnt_mul{0}, cnt_sq{0};
 
 // "shared memory": the window handed out by __cvta_generic_to_shared is addressed by 32-bit offsets, as on the device
 static thread_local char *shared_base = nullptr;

@@ -156,6 +156,15 @@ def rewrite_launches(text):
     return text, count
 
 
+COUNT_OLD = """#if defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
+static unsigned long edg_cnt_mul = 0, edg_cnt_sq = 0;"""
+COUNT_NEW = """#if defined(EDG_EMUL_COUNT)       /* (inserted by ptx_rewrite.py) the SIMT emulator counts field operations of the real kernels */
+#define EDG_COUNT_MUL() ((void)edg_ptx::cnt_mul.fetch_add(1, std::memory_order_relaxed))
+#define EDG_COUNT_SQ() ((void)edg_ptx::cnt_sq.fetch_add(1, std::memory_order_relaxed))
+#elif defined(EDG_COUNT_OPS) && !defined(__CUDA_ARCH__)
+static unsigned long edg_cnt_mul = 0, edg_cnt_sq = 0;"""
+
+
 def main(src, dst):
     os.makedirs(dst, exist_ok=True)
     total = 0
@@ -164,6 +173,9 @@ def main(src, dst):
         if f.endswith((".cuh", ".h", ".cu")):
             new, n = rewrite(open(os.path.join(src, f)).read(), f)
             total += n
+            if f == "fe.cuh":
+                assert new.count(COUNT_OLD) == 1
+                new = new.replace(COUNT_OLD, COUNT_NEW)
             if f.endswith(".cu"):
                 new, k = rewrite_launches(new)
                 launches += k

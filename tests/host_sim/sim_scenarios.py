@@ -1029,6 +1029,38 @@ def scenario_real_kernels_full_scalars():
     sim.clean()
 
 
+def scenario_real_kernels_opcount():
+    """Field operations the REAL verify kernels execute per signature, counted by the emulator (a lane of the loop kernel runs its
+    warp's maximum window count, as on the device): the figure the integer-multiply roofline of bench.py is computed from."""
+    import bench
+    from cpu_ref import best_cpu_impl
+    assert "sim_kernels" in SIM_SO
+    sim, cpu = Sim(), best_cpu_impl()
+    ed, L = sim.ed, sim.L
+    r = rng(23)
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+    base = 512
+    sec, pub, msgs, off, sig = make_signed(cpu, r, base, fixed_len=64)
+    reps = n // base
+    sec, pub, sig, msgs = np.tile(sec, (reps, 1)), np.tile(pub, (reps, 1)), np.tile(sig, (reps, 1)), np.tile(msgs, reps)
+    # different challenges for every row: distinct messages need distinct signatures — sign on the emulated kernels themselves
+    msgs = r.integers(0, 256, size=n * 64, dtype=np.uint8)
+    sig = ed.ed25519_sign_batch(sec, pub, msgs, None, 64)
+    ed.init()
+    m, s = ctypes.c_ulonglong(), ctypes.c_ulonglong()
+    L.edg_emul_counts(ctypes.byref(m), ctypes.byref(s), 1)
+    assert ed.ed25519_verify_batch(sig, pub, msgs, None, 64).all()
+    L.edg_emul_counts(ctypes.byref(m), ctypes.byref(s), 1)
+    per_m, per_s = m.value / n, s.value / n
+    nwin = (per_m - 267) / 28
+    model_m, model_s = bench.OURS_FM["verify"]
+    wide = 72 * per_m + 44 * per_s
+    print(f"verify on the real kernels, {n} signatures: {per_m:.1f} M + {per_s:.1f} S per signature = {nwin:.2f} windows per lane; "
+          f"{wide:.0f} wide multiplies (bench.py model: {model_m:.1f} M + {model_s:.1f} S = {72 * model_m + 44 * model_s:.0f})")
+    assert abs((per_s - 494) / 16 - nwin) < 1e-6                         # both counts describe the same window count
+    assert abs(wide / (72 * model_m + 44 * model_s) - 1) < 0.01          # the roofline's work figure, within 1 %
+
+
 def scenario_no_device():
     """No usable device: the batch calls report it (there is no CPU path to fall back to)."""
     assert os.environ.get("CUDASIM_DEVICES") == "0"

@@ -96,6 +96,13 @@ inline void launch(dim3 grid, dim3 block, size_t smem, void *stream, std::functi
 
 }  // namespace edg_simt
 
+// field operations executed by the kernels since the last reset (builds with -DEDG_EMUL_COUNT)
+extern "C" __attribute__((weak, visibility("default"))) void edg_emul_counts(unsigned long long *mul, unsigned long long *sq, int reset) {
+    *mul = edg_ptx::cnt_mul.load();
+    *sq = edg_ptx::cnt_sq.load();
+    if (reset) { edg_ptx::cnt_mul = 0; edg_ptx::cnt_sq = 0; }
+}
+
 #define threadIdx (edg_simt::cur->tid)
 #define blockIdx (edg_simt::cur->bid)
 #define blockDim (edg_simt::cur->bdim)

@@ -51,6 +51,8 @@ def simlib():
         _PREFETCHED[_key(name, env, args)] = pool.submit(_run, name, env, args)
     for name, env in REAL_KERNEL_RUNS:
         _PREFETCHED[_key(name, env, (), KERNELS_SO)] = pool.submit(_run, name, env, (), KERNELS_SO)
+    _PREFETCHED[_key("real_kernels_opcount", {"CUDASIM_DEVICES": "1"}, ("2048",), KERNELS_SO)] = pool.submit(
+        _run, "real_kernels_opcount", {"CUDASIM_DEVICES": "1"}, ("2048",), KERNELS_SO)
     import tempfile
     scratch = tempfile.mkdtemp(prefix="eddsa_mutants_")
     for index in range(len(MUTANTS)):
@@ -133,6 +135,14 @@ def test_real_kernels_on_the_simt_emulator(simlib, name, env):
     the device-built tables, SHA block-boundary lengths at odd alignments, the full-length fallback.  Bit-exact, without a GPU."""
     res = run_scenario(name, env, so=KERNELS_SO)
     assert res.returncode == 0 and f"OK {name}" in res.stdout, res.stdout[-3000:]
+
+
+def test_roofline_work_figure_counted_on_the_real_kernels(simlib):
+    """Field operations per signature executed by the shipped verify kernels (a lane runs its warp's maximum window count after the
+    permutation), counted by the emulator: within 1 % of the figure bench.py's integer-multiply roofline uses (16 384 signatures:
+    130 991 vs 130 992 wide multiplies, profiles/r02_notes.md)."""
+    res = run_scenario("real_kernels_opcount", {"CUDASIM_DEVICES": "1"}, args=("2048",), so=KERNELS_SO)
+    assert res.returncode == 0 and "OK real_kernels_opcount" in res.stdout, res.stdout[-3000:]
 
 
 def test_kernels_wipe_their_scratch(simlib, tmp_path):
