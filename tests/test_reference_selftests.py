@@ -49,6 +49,26 @@ def test_library_carries_the_reference_soname():
     assert "Library soname: [libeddsa.so.0]" in out
 
 
+@pytest.mark.parametrize("test", TESTS)
+def test_reference_selftests_with_the_host_layer_on_the_simulator(test, tmp_path):
+    """No GPU: the same unmodified binaries with libeddsa.so.0 -> tests/host_sim/libeddsa_sim.so — the product's host layer
+    (host.c, every call a batch of one through its whole pipeline) on the CUDA runtime simulator, whose kernels run the per-thread
+    operation bodies of ops.cuh.  Test infrastructure; the product itself has no CPU path."""
+    _need_binaries()
+    hs = os.path.join(ROOT, "tests", "host_sim")
+    subprocess.run(["make", "-s", "-C", hs, "libeddsa_sim.so"], check=True)
+    os.symlink(os.path.join(hs, "libeddsa_sim.so"), tmp_path / "libeddsa.so.0")
+    env_keep = {k: os.environ.pop(k) for k in list(os.environ) if k.startswith(("CUDASIM_", "EDDSA_B200_"))}
+    os.environ["CUDASIM_DEVICES"] = "1"
+    try:
+        resolved, res = _run(test, str(tmp_path))
+    finally:
+        del os.environ["CUDASIM_DEVICES"]
+        os.environ.update(env_keep)
+    assert resolved == os.path.realpath(os.path.join(hs, "libeddsa_sim.so"))
+    assert res.returncode == 0, res.stderr
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("test", TESTS)
 def test_reference_selftests_with_b200_library(test, tmp_path):
