@@ -1059,6 +1059,28 @@ def scenario_real_kernels_opcount():
           f"{wide:.0f} wide multiplies (bench.py model: {model_m:.1f} M + {model_s:.1f} S = {72 * model_m + 44 * model_s:.0f})")
     assert abs((per_s - 494) / 16 - nwin) < 1e-6                         # both counts describe the same window count
     assert abs(wide / (72 * model_m + 44 * model_s) - 1) < 0.01          # the roofline's work figure, within 1 %
+    if len(sys.argv) > 3 and sys.argv[3] == "all":
+        # the operations with a shared inversion: bench.py's ours_fm(op, n) with the emulated device's resident threads (2 SMs: 1024
+        # comb threads, 1024 ladder threads) must give exactly what the kernels execute
+        resident = {"genpub": 1024, "sign": 1024, "x25519_base": 1024, "x25519": 1024}
+        k = 8192
+        ksec = rand_rows(r, k)
+        kpub = cpu.genpub(ksec)
+        kmsg = r.integers(0, 256, size=k * 64, dtype=np.uint8)
+        pts = rand_rows(r, k)
+        runs = {"genpub": lambda: ed.ed25519_genpub_batch(ksec), "sign": lambda: ed.ed25519_sign_batch(ksec, kpub, kmsg, None, 64),
+                "x25519_base": lambda: ed.x25519_base_batch(ksec), "x25519": lambda: ed.x25519_batch(ksec[:4096], pts[:4096])}
+        for op, fn in runs.items():
+            cnt = 4096 if op == "x25519" else k
+            L.edg_emul_counts(ctypes.byref(m), ctypes.byref(s), 1)
+            fn()
+            L.edg_emul_counts(ctypes.byref(m), ctypes.byref(s), 1)
+            mm, ss = bench.OURS_FM_SINGLE[op]
+            share = cnt / resident[op]
+            want = (mm - 11 + 11 / share + 3, ss - 254 + 254 / share)
+            print(f"{op}: {m.value / cnt:.3f} M + {s.value / cnt:.3f} S per operation on the real kernels, inversion shared by {share:.0f}; "
+                  f"bench.py's formula: {want[0]:.3f} M + {want[1]:.3f} S")
+            assert abs(m.value / cnt - want[0]) < 1e-6 and abs(s.value / cnt - want[1]) < 1e-6, op
 
 
 def scenario_no_device():
